@@ -1,0 +1,204 @@
+/*
+ * lbm_b200.h — C ABI of the B200-native D3Q19 BGK collide-and-stream path.
+ *
+ * This is the drop-in boundary for the one hot path of blackwut/LBMCL.  The reference has no
+ * plugin/FFI interface: its host class LBMCL<T> (reference lbmcl.hpp) talks to the device through
+ * the OpenCL C++ bindings wrapped by libs/CLUtil.hpp.  Every entry point below names the reference
+ * call(s) it stands in for (paths relative to the reference tree), so that lbmcl.hpp could be
+ * re-pointed at this library call by call.
+ *
+ * Conventions
+ *   - plain C types only; no device pointers cross the ABI except where a function says so
+ *     explicitly (the multi-process halo plumbing at the end);
+ *   - every call returns LBM_OK (0) or a negative lbm_status; the message of the last failure on a
+ *     context is available from lbm_last_error() (the reference prints "file:line what(code) - NAME"
+ *     and exits, CLUtil.hpp:83-117; here the ABI never exits or throws — the host decides);
+ *   - a context is driven by one host thread at a time (the reference has one in-order queue,
+ *     CLUtil.hpp:190-199);
+ *   - there is no CPU fallback: if no CUDA device is usable, lbm_create fails.
+ *
+ * Lattice conventions (identical to the reference): cube of DIM^3 cells, DIM a power of two,
+ * linear cell id = x + y*DIM + z*DIM^2 (kernels.cl:67), outer one-cell WALL shell, D3Q19 direction
+ * numbering of kernels.cl:131-205, CSoA(stride) population layout of kernels.cl:64.
+ */
+#ifndef LBM_B200_H
+#define LBM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LBM_B200_ABI_VERSION 1
+
+typedef enum lbm_status {
+    LBM_OK = 0,
+    LBM_ERR_INVALID = -1,     /* bad argument / unsupported configuration          */
+    LBM_ERR_CUDA = -2,        /* a CUDA runtime call failed (message has the name) */
+    LBM_ERR_NO_DEVICE = -3,   /* no usable CUDA device: there is no CPU fallback   */
+    LBM_ERR_OOM = -4,         /* device or host allocation failed                  */
+    LBM_ERR_STATE = -5        /* call made in the wrong order                      */
+} lbm_status;
+
+typedef enum lbm_precision { LBM_F32 = 0, LBM_F64 = 1 } lbm_precision;
+
+/* Kernel organisation.  All variants compute the same function. */
+typedef enum lbm_variant {
+    LBM_VARIANT_AUTO = 0,   /* widest vector variant the stride allows                          */
+    LBM_VARIANT_SCALAR = 1, /* two-lattice pull, one cell per thread                             */
+    LBM_VARIANT_VEC2 = 2,   /* two-lattice pull, 2 cells per thread, x shifts by warp shuffle    */
+    LBM_VARIANT_VEC4 = 4    /* two-lattice pull, 4 cells per thread (128-bit fp32 access)        */
+} lbm_variant;
+
+/*
+ * Configuration of one context = one device = one z-slab of the cube.
+ * Stands in for the LBMCL<T> constructor arguments (lbmcl.hpp:338-388), the -D kernel build options
+ * (lbmcl.hpp:131-156) and the device choice (CLUtil.hpp:119-178).
+ */
+typedef struct lbm_params {
+    int32_t abi_version;   /* must be LBM_B200_ABI_VERSION                                         */
+    int32_t dim;           /* cube edge, power of two, >= 4   (-d; lbmcl.hpp:364-367)              */
+    int32_t precision;     /* lbm_precision                   (-F; main.cpp:44-48)                 */
+    int32_t fast_math;     /* 0 strict IEEE op order, 1 contracted / approximate division
+                              (-o, "-cl-fast-relaxed-math", lbmcl.hpp:151-153)                      */
+    double viscosity;      /* as given on the command line; the library applies the reference's
+                              6-significant-digit text round trip (lbmcl.hpp:140-141)   */
+    double velocity;       /* lid speed, same round trip                                            */
+    int64_t stride;        /* CSoA stride, power of two, 1 .. DIM^3 (-s; lbmcl.hpp:384-387)         */
+    int32_t block_x;       /* requested work-group shape (-w; lbmcl.hpp:371-382); a hint: the       */
+    int32_t block_y;       /*   library clamps it to a legal CUDA block (see lbm_block_shape)       */
+    int32_t block_z;
+    int32_t device;        /* CUDA ordinal (-D); <0 = current device                                */
+    int32_t variant;       /* lbm_variant                                                           */
+    int32_t z_begin;       /* owned global planes [z_begin, z_end); 0, DIM for a single device      */
+    int32_t z_end;
+    int32_t reserved[8];   /* must be zero                                                          */
+} lbm_params;
+
+typedef struct lbm_ctx lbm_ctx;
+
+/* Fill *p with the reference's defaults (lbm_options.hpp:32-50): dim 8, nu 0.0089, U 0.05,
+ * stride 32, work group 8,8,8, fp32, strict math, whole cube on the current device. */
+void lbm_default_params(lbm_params *p);
+
+/* Device selection + context + queue + program build + the five buffers
+ * (lbmcl.hpp:392-417 setupSimulation; CLUtil.hpp:119-229).  Allocates two f lattices, rho, u. */
+int lbm_create(const lbm_params *p, lbm_ctx **out);
+
+/* Releases everything the context owns (the cl::Buffer / cl::Kernel destructors, lbmcl.hpp:672). */
+void lbm_destroy(lbm_ctx *ctx);
+
+/* Message of the last failure on ctx (or of the last failed lbm_create when ctx is NULL). */
+const char *lbm_last_error(const lbm_ctx *ctx);
+
+/* enqueue of the `initialize` kernel (lbmcl.hpp:493-498; kernels.cl:277-318).  Asynchronous.
+ * Resets the iteration counter to 0. */
+int lbm_init(lbm_ctx *ctx);
+
+/* enqueue of ONE `compute` launch = one iteration (lbmcl.hpp:505-511; kernels.cl:321-425) with the
+ * reference's update_macro flag (lbmcl.hpp:436, 461).  Asynchronous; an event pair is recorded so
+ * that the launch is counted by lbm_time_ms exactly like a reference "compute" event. */
+int lbm_step(lbm_ctx *ctx, int update_macro);
+
+/* The loop of lbmcl.hpp:505-511 without the readbacks: n_iterations launches, iteration numbers
+ * continuing from the context's counter, update_macro = (every != 0 && it % every == 0).
+ * Asynchronous.  One event pair brackets the whole batch. */
+int lbm_run(lbm_ctx *ctx, int n_iterations, int every);
+
+/* queue.finish() (lbmcl.hpp:525-532). */
+int lbm_sync(lbm_ctx *ctx);
+
+/* Blocking readback of rho and u (lbmcl.hpp:268-277 inside storeData).  rho -> host[N], u ->
+ * host[3][N] with N = DIM^3 in the reference's GLOBAL layout (kernels.cl:67-70); a slab context
+ * writes only its owned planes.  Either pointer may be NULL.  Element type = the context's precision. */
+int lbm_read_macros(lbm_ctx *ctx, void *rho_host, void *u_host);
+
+/* Blocking readback of the cell-type map (lbmcl.hpp:164 inside storeMap), global layout int32[N]. */
+int lbm_read_map(lbm_ctx *ctx, int32_t *map_host);
+
+/* Blocking readback of the population lattice that the NEXT iteration will read, presented as the
+ * reference stores it: pre-collision / post-streaming values in CSoA(stride) order over the whole
+ * cube (lbmcl.hpp:211 inside storeF, called as in lbmcl.hpp:503, 517-519).  host[19*N]. */
+int lbm_read_f(lbm_ctx *ctx, void *f_host);
+
+/* Profiling numbers (CLUtil.hpp:231-243 over the event list, lbmcl.hpp:548-574):
+ * total_ms   = start of `initialize` to end of the last enqueued work,
+ * kernels_ms = sum of the durations of the compute launches only (lbmcl.hpp:568-571).
+ * Synchronises the context. */
+int lbm_time_ms(lbm_ctx *ctx, double *total_ms, double *kernels_ms);
+
+/* CL_DEVICE_NAME (lbmcl.hpp:626, 651). */
+int lbm_device_name(const lbm_ctx *ctx, char *buf, size_t buflen);
+
+/* Effective parameters: what the reference would have compiled into the kernel.
+ * out[0] = viscosity literal, out[1] = velocity literal, out[2] = INV_TAU (kernels.cl:61-62). */
+int lbm_effective_params(const lbm_ctx *ctx, double out[3]);
+
+/* The CUDA block actually used for the compute kernel, the cells per thread, and the
+ * bytes of device memory the context allocated. */
+int lbm_block_shape(const lbm_ctx *ctx, int32_t block[3], int32_t *cells_per_thread);
+int64_t lbm_device_bytes(const lbm_ctx *ctx);
+
+/* Number of compute-kernel launches enqueued since lbm_init (for benchmark bookkeeping). */
+int64_t lbm_launch_count(const lbm_ctx *ctx);
+
+/* Iterations performed since lbm_init. */
+int64_t lbm_iteration(const lbm_ctx *ctx);
+
+/* Run all subsequent work of this context on an existing CUDA stream (a cudaStream_t passed as
+ * void*; NULL restores the context's own stream).  Lets a host that already owns a stream — e.g. the
+ * Python benchmark's torch stream — time the kernels with its own events. */
+int lbm_set_stream(lbm_ctx *ctx, void *cuda_stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * z-slab decomposition (new functionality; the reference is single-device).
+ *
+ * A context created with 0 < z_begin or z_end < DIM owns planes [z_begin, z_end) and stores one
+ * extra halo plane per interior face.  Per iteration only the 5 populations that cross a face
+ * travel: upward (e_z = +1) q = 6,15,16,17,18 and downward (e_z = -1) q = 5,11,12,13,14.
+ *
+ * Two transports:
+ *  (1) same process, peer access: lbm_link_peers() gives each context its neighbours; lbm_step /
+ *      lbm_run on the group then write the crossing populations straight into the neighbour's halo
+ *      plane from inside the boundary-plane kernel (NVLink stores) and order the devices with
+ *      events.  Use lbm_group_* below.
+ *  (2) one process per device (torchrun): the host moves packed halos itself (NCCL send/recv).
+ *      lbm_halo_pack() fills the two dense send buffers from the lattice the next iteration reads,
+ *      lbm_halo_unpack() scatters the two dense receive buffers into the halo planes.  The four
+ *      buffers are DEVICE pointers owned by the context (5*DIM^2 elements each), exposed so that the
+ *      host can hand them to its communication library.
+ * ------------------------------------------------------------------------------------------------ */
+
+typedef enum lbm_face { LBM_FACE_LOW = 0, LBM_FACE_HIGH = 1 } lbm_face;
+
+/* number of elements (not bytes) in one packed halo: 5 * DIM * DIM */
+int64_t lbm_halo_elems(const lbm_ctx *ctx);
+/* device pointers of the dense halo buffers; NULL for a face on the cube boundary */
+void *lbm_halo_send_buffer(lbm_ctx *ctx, int face);
+void *lbm_halo_recv_buffer(lbm_ctx *ctx, int face);
+/* pack the outgoing populations of the owned boundary planes (asynchronous, on the ctx stream) */
+int lbm_halo_pack(lbm_ctx *ctx);
+/* scatter the received populations into the halo planes (asynchronous, on the ctx stream) */
+int lbm_halo_unpack(lbm_ctx *ctx);
+
+/* Same-process group of slab contexts, ordered by z.  lbm_group_create builds n contexts from one
+ * parameter block (z range split evenly over devices[0..n-1]), enables peer access and links
+ * neighbours.  The group calls mirror the single-context ones. */
+typedef struct lbm_group lbm_group;
+int lbm_group_create(const lbm_params *p, const int32_t *devices, int n, lbm_group **out);
+void lbm_group_destroy(lbm_group *g);
+const char *lbm_group_last_error(const lbm_group *g);
+int lbm_group_size(const lbm_group *g);
+lbm_ctx *lbm_group_ctx(lbm_group *g, int i);
+int lbm_group_init(lbm_group *g);
+int lbm_group_run(lbm_group *g, int n_iterations, int every);
+int lbm_group_sync(lbm_group *g);
+int lbm_group_read_macros(lbm_group *g, void *rho_host, void *u_host);
+int lbm_group_time_ms(lbm_group *g, double *total_ms, double *kernels_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LBM_B200_H */

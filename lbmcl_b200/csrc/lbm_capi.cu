@@ -1,0 +1,785 @@
+// C ABI of the B200-native D3Q19 collide-and-stream path (see include/lbm_b200.h).
+//
+// This file replaces what the reference's lbmcl.hpp obtains from libs/CLUtil.hpp + cl.hpp: device
+// selection, buffers, kernel launches with the ping-pong binding, readbacks and event timing.
+// There is no CPU fallback anywhere in here: without a CUDA device lbm_create fails.
+#include "../../include/lbm_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "lbm_kernels.cuh"
+
+using namespace lbm;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct EventPair {
+    cudaEvent_t start = nullptr;
+    cudaEvent_t stop = nullptr;
+};
+
+}  // namespace
+
+struct lbm_ctx {
+    lbm_params p{};
+    int device = 0;
+    std::string device_name;
+    std::string error;
+
+    // geometry of the slab
+    int dim = 0;
+    int z_begin = 0, z_end = 0;  // owned planes
+    int zs0 = 0;                 // global z of stored plane 0
+    int nz_local = 0;            // stored planes (owned + halos)
+    long long n_local = 0;       // stored cells
+    long long n_alloc = 0;       // stored cells rounded up to a multiple of the stride
+    Layout lay{};
+    int vec = 1;
+    dim3 block{1, 1, 1};
+    size_t esize = 4;
+
+    // effective constants (after the reference's text round trip)
+    double eff_viscosity = 0, eff_velocity = 0, eff_inv_tau = 0;
+    Consts<float> cf{};
+    Consts<double> cd{};
+    float stale_f[2][Q]{};
+    double stale_d[2][Q]{};
+
+    // device memory
+    void *f[2] = {nullptr, nullptr};  // the two lattices
+    void *rho = nullptr;
+    void *u = nullptr;
+    void *halo_send[2] = {nullptr, nullptr};
+    void *halo_recv[2] = {nullptr, nullptr};
+    int64_t device_bytes = 0;
+    int cur = 0;  // index of the lattice the NEXT iteration reads
+
+    // same-process neighbours (lbm_group)
+    lbm_ctx *peer[2] = {nullptr, nullptr};
+
+    // execution
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    int64_t iteration = 0;
+    int64_t launches = 0;
+    bool initialised = false;
+
+    // profiling (the reference's event list, lbmcl.hpp:74)
+    cudaEvent_t ev_init_start = nullptr;
+    cudaEvent_t ev_last = nullptr;
+    std::vector<EventPair> compute_events;
+    double kernels_ms_accum = 0.0;  // folded-in pairs
+};
+
+namespace {
+
+int fail(lbm_ctx *ctx, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->error = buf;
+    else g_create_error = buf;
+    return code;
+}
+
+#define LBM_CUDA(ctx, ...)                                                                              \
+    do {                                                                                                \
+        cudaError_t e__ = (__VA_ARGS__);                                                                \
+        if (e__ != cudaSuccess)                                                                         \
+            return fail((ctx), e__ == cudaErrorMemoryAllocation ? LBM_ERR_OOM : LBM_ERR_CUDA,           \
+                        "%s:%d %s(%d) - %s", __FILE__, __LINE__, #__VA_ARGS__, (int)e__, cudaGetErrorName(e__)); \
+    } while (0)
+
+bool is_pow2(long long v) { return v > 0 && (v & (v - 1)) == 0; }
+int ilog2(long long v)
+{
+    int n = 0;
+    while (v > 1) { v >>= 1; ++n; }
+    return n;
+}
+int floor_pow2(int v)
+{
+    int p = 1;
+    while (p * 2 <= v) p *= 2;
+    return p;
+}
+
+// lbmcl.hpp:140-141 + kernels.cl:61-62: the value printed with 6 significant digits by operator<<
+// from a T-typed member is what the kernel compiler parses back as a T literal.
+template <typename T>
+T text_roundtrip(double v);
+template <>
+float text_roundtrip<float>(double v)
+{
+    char buf[64];
+    snprintf(buf, sizeof buf, "%g", (double)(float)v);
+    return strtof(buf, nullptr);
+}
+template <>
+double text_roundtrip<double>(double v)
+{
+    char buf[64];
+    snprintf(buf, sizeof buf, "%g", v);
+    return strtod(buf, nullptr);
+}
+
+// Folded in T arithmetic exactly like the reference's compile-time constants.  `volatile` keeps the
+// host compiler from contracting 3*nu + 0.5 into an FMA whatever its flags are.
+template <typename T>
+Consts<T> make_consts(double nu, double u_lid, double *eff)
+{
+    Consts<T> c;
+    volatile T visc = text_roundtrip<T>(nu);
+    volatile T three_nu = T(3.0) * visc;
+    volatile T tau = three_nu + T(0.5);
+    c.u_lid = text_roundtrip<T>(u_lid);
+    c.inv_tau = T(1.0) / tau;
+    c.w[0] = T(1.0) / T(3.0);
+    c.w[1] = T(1.0) / T(18.0);
+    c.w[2] = T(1.0) / T(36.0);
+    eff[0] = (double)visc;
+    eff[1] = (double)c.u_lid;
+    eff[2] = (double)c.inv_tau;
+    return c;
+}
+
+template <typename T>
+StepArgs<T> make_step_args(lbm_ctx *c, int z_begin, int z_end, const Consts<T> &k, const T (&stale)[2][Q])
+{
+    StepArgs<T> a{};
+    a.dst = static_cast<T *>(c->f[c->cur ^ 1]);
+    a.src = static_cast<const T *>(c->f[c->cur]);
+    a.rho = static_cast<T *>(c->rho);
+    a.u = static_cast<T *>(c->u);
+    a.peer_lo = nullptr;
+    a.peer_hi = nullptr;
+    if (c->peer[0]) {
+        // my first owned plane is the neighbour's high halo plane, in the lattice it reads next
+        lbm_ctx *n = c->peer[0];
+        a.peer_lo = static_cast<T *>(n->f[n->cur ^ 1]);
+        a.peer_lo_plane = c->z_begin - n->zs0;
+    }
+    if (c->peer[1]) {
+        lbm_ctx *n = c->peer[1];
+        a.peer_hi = static_cast<T *>(n->f[n->cur ^ 1]);
+        a.peer_hi_plane = (c->z_end - 1) - n->zs0;
+    }
+    a.z_own_begin = c->z_begin;
+    a.z_own_end = c->z_end;
+    a.dim = c->dim;
+    a.zs0 = c->zs0;
+    a.z_begin = z_begin;
+    a.z_end = z_end;
+    a.n_local = c->n_local;
+    a.lay = c->lay;
+    a.c = k;
+    for (int i = 0; i < 2; ++i)
+        for (int q = 0; q < Q; ++q) a.stale[i][q] = stale[i][q];
+    return a;
+}
+
+template <typename T, int VEC>
+cudaError_t launch_step_t(lbm_ctx *c, const StepArgs<T> &a, bool macro, bool peer, cudaStream_t s)
+{
+    const int nz = a.z_end - a.z_begin;
+    if (nz <= 0) return cudaSuccess;
+    const dim3 b = c->block;
+    const dim3 g((unsigned)(c->dim / (b.x * VEC)), (unsigned)(c->dim / b.y), (unsigned)((nz + b.z - 1) / b.z));
+    const bool fast = c->p.fast_math != 0;
+#define LBM_LAUNCH(F, M, P) step_pull_kernel<T, VEC, F, M, P><<<g, b, 0, s>>>(a)
+    if (peer) {
+        if (fast) { if (macro) LBM_LAUNCH(true, true, true); else LBM_LAUNCH(true, false, true); }
+        else      { if (macro) LBM_LAUNCH(false, true, true); else LBM_LAUNCH(false, false, true); }
+    } else {
+        if (fast) { if (macro) LBM_LAUNCH(true, true, false); else LBM_LAUNCH(true, false, false); }
+        else      { if (macro) LBM_LAUNCH(false, true, false); else LBM_LAUNCH(false, false, false); }
+    }
+#undef LBM_LAUNCH
+    c->launches += 1;
+    return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_step_p(lbm_ctx *c, int z_begin, int z_end, bool macro, cudaStream_t s,
+                          const Consts<T> &k, const T (&stale)[2][Q])
+{
+    const StepArgs<T> a = make_step_args<T>(c, z_begin, z_end, k, stale);
+    const bool peer = (a.peer_lo != nullptr && z_begin <= c->z_begin && c->z_begin < z_end) ||
+                      (a.peer_hi != nullptr && z_begin <= c->z_end - 1 && c->z_end - 1 < z_end);
+    switch (c->vec) {
+        case 4:
+            if constexpr (sizeof(T) == 4) return launch_step_t<T, 4>(c, a, macro, peer, s);
+            else return cudaErrorInvalidValue;
+        case 2: return launch_step_t<T, 2>(c, a, macro, peer, s);
+        default: return launch_step_t<T, 1>(c, a, macro, peer, s);
+    }
+}
+
+// one launch of the step kernel over global planes [z_begin, z_end) (clipped to the computed range)
+cudaError_t launch_step(lbm_ctx *c, int z_begin, int z_end, bool macro, cudaStream_t s)
+{
+    if (c->p.precision == LBM_F32) return launch_step_p<float>(c, z_begin, z_end, macro, s, c->cf, c->stale_f);
+    return launch_step_p<double>(c, z_begin, z_end, macro, s, c->cd, c->stale_d);
+}
+
+template <typename T>
+cudaError_t launch_init_t(lbm_ctx *c, const Consts<T> &k, cudaStream_t s)
+{
+    InitArgs<T> a{};
+    a.f0 = static_cast<T *>(c->f[0]);
+    a.f1 = static_cast<T *>(c->f[1]);
+    a.rho = static_cast<T *>(c->rho);
+    a.u = static_cast<T *>(c->u);
+    a.dim = c->dim;
+    a.zs0 = c->zs0;
+    a.nz_local = c->nz_local;
+    a.n_local = c->n_local;
+    a.lay = c->lay;
+    a.c = k;
+    const int bx = c->dim < 64 ? c->dim : 64;
+    const int by = (256 / bx) < c->dim ? (256 / bx) : c->dim;
+    const dim3 b(bx, by, 1);
+    const dim3 g(c->dim / bx, c->dim / by, c->nz_local);
+    init_kernel<T><<<g, b, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+template <typename T>
+int compute_stale(lbm_ctx *c, const Consts<T> &k, T (&stale)[2][Q])
+{
+    T *d = nullptr;
+    LBM_CUDA(c, cudaMalloc(&d, sizeof(T) * 2 * Q));
+    stale_kernel<T><<<1, 1, 0, c->stream>>>(k, d);
+    LBM_CUDA(c, cudaGetLastError());
+    LBM_CUDA(c, cudaMemcpyAsync(&stale[0][0], d, sizeof(T) * 2 * Q, cudaMemcpyDeviceToHost, c->stream));
+    LBM_CUDA(c, cudaStreamSynchronize(c->stream));
+    LBM_CUDA(c, cudaFree(d));
+    return LBM_OK;
+}
+
+// Choose the CUDA block from the requested work-group shape: powers of two, bx*VEC | DIM, by | DIM,
+// at most 256 threads (the kernels are compiled with __launch_bounds__(256)).
+void choose_block(lbm_ctx *c)
+{
+    const int dim = c->dim;
+    int bx = floor_pow2(c->p.block_x > 0 ? c->p.block_x : 1) / c->vec;
+    if (bx < 1) bx = 1;
+    if (bx > dim / c->vec) bx = dim / c->vec;
+    int by = floor_pow2(c->p.block_y > 0 ? c->p.block_y : 1);
+    if (by > dim) by = dim;
+    int bz = floor_pow2(c->p.block_z > 0 ? c->p.block_z : 1);
+    if (bz > dim) bz = dim;
+    if (bz > 64) bz = 64;
+    while (bx * by * bz > 256) {
+        if (bz > 1) bz /= 2;
+        else if (by > 1) by /= 2;
+        else bx /= 2;
+    }
+    c->block = dim3(bx, by, bz);
+}
+
+int record_last(lbm_ctx *c)
+{
+    LBM_CUDA(c, cudaEventRecord(c->ev_last, c->stream));
+    return LBM_OK;
+}
+
+int use_device(lbm_ctx *c)
+{
+    LBM_CUDA(c, cudaSetDevice(c->device));
+    return LBM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void lbm_default_params(lbm_params *p)
+{
+    if (!p) return;
+    std::memset(p, 0, sizeof *p);
+    p->abi_version = LBM_B200_ABI_VERSION;
+    p->dim = 8;            // lbm_options.hpp:35
+    p->precision = LBM_F32;
+    p->fast_math = 0;      // lbm_options.hpp:45
+    p->viscosity = 0.0089; // lbm_options.hpp:36
+    p->velocity = 0.05;    // lbm_options.hpp:37
+    p->stride = 32;        // lbm_options.hpp:43
+    p->block_x = 8;        // lbm_options.hpp:40-42
+    p->block_y = 8;
+    p->block_z = 8;
+    p->device = -1;
+    p->variant = LBM_VARIANT_AUTO;
+    p->z_begin = 0;
+    p->z_end = 0;          // 0 = whole cube
+}
+
+const char *lbm_last_error(const lbm_ctx *ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+void lbm_destroy(lbm_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->own_stream) cudaStreamSynchronize(c->own_stream);
+    for (auto &e : c->compute_events) {
+        if (e.start) cudaEventDestroy(e.start);
+        if (e.stop) cudaEventDestroy(e.stop);
+    }
+    if (c->ev_init_start) cudaEventDestroy(c->ev_init_start);
+    if (c->ev_last) cudaEventDestroy(c->ev_last);
+    for (int i = 0; i < 2; ++i) {
+        if (c->f[i]) cudaFree(c->f[i]);
+        if (c->halo_send[i]) cudaFree(c->halo_send[i]);
+        if (c->halo_recv[i]) cudaFree(c->halo_recv[i]);
+    }
+    if (c->rho) cudaFree(c->rho);
+    if (c->u) cudaFree(c->u);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+int lbm_create(const lbm_params *p, lbm_ctx **out)
+{
+    if (!out) return fail(nullptr, LBM_ERR_INVALID, "lbm_create: out is NULL");
+    *out = nullptr;
+    if (!p) return fail(nullptr, LBM_ERR_INVALID, "lbm_create: params is NULL");
+    if (p->abi_version != LBM_B200_ABI_VERSION)
+        return fail(nullptr, LBM_ERR_INVALID, "lbm_create: abi_version %d, library is %d", p->abi_version,
+                    LBM_B200_ABI_VERSION);
+    if (p->dim < 4 || !is_pow2(p->dim) || p->dim > 2048)
+        return fail(nullptr, LBM_ERR_INVALID, "lbm_create: dim %d must be a power of two in [4, 2048]", p->dim);
+    if (p->precision != LBM_F32 && p->precision != LBM_F64)
+        return fail(nullptr, LBM_ERR_INVALID, "lbm_create: unknown precision %d", p->precision);
+    const long long n_cube = (long long)p->dim * p->dim * p->dim;
+    if (!is_pow2(p->stride) || p->stride > n_cube)
+        return fail(nullptr, LBM_ERR_INVALID,
+                    "lbm_create: stride %lld must be a power of two in [1, dim^3] (the reference overruns its "
+                    "buffers beyond that, kernels.cl:64)", (long long)p->stride);
+    if (!(p->viscosity >= 0.0) || !std::isfinite(p->viscosity) || !std::isfinite(p->velocity))
+        return fail(nullptr, LBM_ERR_INVALID, "lbm_create: viscosity/velocity must be finite, viscosity >= 0");
+    int zb = p->z_begin, ze = p->z_end;
+    if (zb == 0 && ze == 0) ze = p->dim;
+    if (zb < 0 || ze > p->dim || zb >= ze)
+        return fail(nullptr, LBM_ERR_INVALID, "lbm_create: bad z range [%d, %d)", zb, ze);
+    switch (p->variant) {
+        case LBM_VARIANT_AUTO: case LBM_VARIANT_SCALAR: case LBM_VARIANT_VEC2: case LBM_VARIANT_VEC4: break;
+        default: return fail(nullptr, LBM_ERR_INVALID, "lbm_create: unknown variant %d", p->variant);
+    }
+
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0)
+        return fail(nullptr, LBM_ERR_NO_DEVICE, "lbm_create: no CUDA device (%s); this library has no CPU path",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorName(e));
+
+    lbm_ctx *c = new (std::nothrow) lbm_ctx();
+    if (!c) return fail(nullptr, LBM_ERR_OOM, "lbm_create: host allocation failed");
+    c->p = *p;
+    int rc = LBM_OK;
+    auto bail = [&](int code) {
+        g_create_error = c->error;
+        lbm_destroy(c);
+        return code;
+    };
+
+    if (p->device >= 0) c->device = p->device;
+    else if (cudaGetDevice(&c->device) != cudaSuccess) c->device = 0;
+    if (c->device >= n_dev) {
+        fail(c, LBM_ERR_NO_DEVICE, "lbm_create: device %d requested, %d present", c->device, n_dev);
+        return bail(LBM_ERR_NO_DEVICE);
+    }
+    if ((rc = use_device(c)) != LBM_OK) return bail(rc);
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, c->device) != cudaSuccess) {
+        fail(c, LBM_ERR_CUDA, "lbm_create: cudaGetDeviceProperties failed");
+        return bail(LBM_ERR_CUDA);
+    }
+    c->device_name = prop.name;
+
+    c->dim = p->dim;
+    c->z_begin = zb;
+    c->z_end = ze;
+    c->zs0 = zb > 0 ? zb - 1 : 0;
+    const int zs1 = ze < p->dim ? ze + 1 : p->dim;
+    c->nz_local = zs1 - c->zs0;
+    c->n_local = (long long)c->nz_local * p->dim * p->dim;
+    c->lay.sdiv = ilog2(p->stride);
+    c->lay.smod = p->stride - 1;
+    c->n_alloc = ((c->n_local + p->stride - 1) / p->stride) * p->stride;
+    c->esize = p->precision == LBM_F32 ? 4 : 8;
+
+    // widest vector the stride, the row length and the precision allow (16-byte accesses)
+    const int vmax = p->precision == LBM_F32 ? 4 : 2;
+    int vec = p->variant == LBM_VARIANT_AUTO ? vmax : (p->variant == LBM_VARIANT_SCALAR ? 1 : p->variant);
+    if (vec > vmax) vec = vmax;
+    while (vec > 1 && (p->stride % vec != 0 || p->dim % vec != 0)) vec /= 2;
+    c->vec = vec;
+    choose_block(c);
+
+    double eff[3];
+    c->cf = make_consts<float>(p->viscosity, p->velocity, eff);
+    if (p->precision == LBM_F32) { c->eff_viscosity = eff[0]; c->eff_velocity = eff[1]; c->eff_inv_tau = eff[2]; }
+    c->cd = make_consts<double>(p->viscosity, p->velocity, eff);
+    if (p->precision == LBM_F64) { c->eff_viscosity = eff[0]; c->eff_velocity = eff[1]; c->eff_inv_tau = eff[2]; }
+
+    auto cuda_or_bail = [&](cudaError_t err, const char *what) {
+        if (err == cudaSuccess) return false;
+        fail(c, err == cudaErrorMemoryAllocation ? LBM_ERR_OOM : LBM_ERR_CUDA, "lbm_create: %s(%d) - %s", what,
+             (int)err, cudaGetErrorName(err));
+        return true;
+    };
+    if (cuda_or_bail(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking), "cudaStreamCreate"))
+        return bail(LBM_ERR_CUDA);
+    c->stream = c->own_stream;
+    if (cuda_or_bail(cudaEventCreate(&c->ev_init_start), "cudaEventCreate")) return bail(LBM_ERR_CUDA);
+    if (cuda_or_bail(cudaEventCreate(&c->ev_last), "cudaEventCreate")) return bail(LBM_ERR_CUDA);
+
+    const size_t f_bytes = (size_t)c->n_alloc * Q * c->esize;
+    const size_t m_bytes = (size_t)c->n_local * c->esize;
+    for (int i = 0; i < 2; ++i) {
+        cudaError_t err = cudaMalloc(&c->f[i], f_bytes);
+        if (cuda_or_bail(err, "cudaMalloc(f)")) return bail(err == cudaErrorMemoryAllocation ? LBM_ERR_OOM : LBM_ERR_CUDA);
+        c->device_bytes += (int64_t)f_bytes;
+    }
+    {
+        cudaError_t err = cudaMalloc(&c->rho, m_bytes);
+        if (cuda_or_bail(err, "cudaMalloc(rho)")) return bail(err == cudaErrorMemoryAllocation ? LBM_ERR_OOM : LBM_ERR_CUDA);
+        err = cudaMalloc(&c->u, 3 * m_bytes);
+        if (cuda_or_bail(err, "cudaMalloc(u)")) return bail(err == cudaErrorMemoryAllocation ? LBM_ERR_OOM : LBM_ERR_CUDA);
+        c->device_bytes += (int64_t)(4 * m_bytes);
+    }
+    const size_t h_bytes = (size_t)5 * p->dim * p->dim * c->esize;
+    const bool has_face[2] = { zb > 0, ze < p->dim };
+    for (int fidx = 0; fidx < 2; ++fidx) {
+        if (!has_face[fidx]) continue;
+        if (cuda_or_bail(cudaMalloc(&c->halo_send[fidx], h_bytes), "cudaMalloc(halo)")) return bail(LBM_ERR_OOM);
+        if (cuda_or_bail(cudaMalloc(&c->halo_recv[fidx], h_bytes), "cudaMalloc(halo)")) return bail(LBM_ERR_OOM);
+        c->device_bytes += (int64_t)(2 * h_bytes);
+    }
+
+    if (p->precision == LBM_F32) rc = compute_stale<float>(c, c->cf, c->stale_f);
+    else rc = compute_stale<double>(c, c->cd, c->stale_d);
+    if (rc != LBM_OK) return bail(rc);
+
+    *out = c;
+    return LBM_OK;
+}
+
+int lbm_init(lbm_ctx *c)
+{
+    if (!c) return LBM_ERR_INVALID;
+    int rc = use_device(c);
+    if (rc != LBM_OK) return rc;
+    // a fresh profile, like a fresh LBMCL object (lbmcl.hpp:74)
+    for (auto &e : c->compute_events) {
+        cudaEventDestroy(e.start);
+        cudaEventDestroy(e.stop);
+    }
+    c->compute_events.clear();
+    c->kernels_ms_accum = 0.0;
+    LBM_CUDA(c, cudaEventRecord(c->ev_init_start, c->stream));
+    if (c->p.precision == LBM_F32) LBM_CUDA(c, launch_init_t<float>(c, c->cf, c->stream));
+    else LBM_CUDA(c, launch_init_t<double>(c, c->cd, c->stream));
+    c->cur = 0;
+    c->iteration = 0;
+    c->launches = 0;
+    c->initialised = true;
+    return record_last(c);
+}
+
+static int push_pair(lbm_ctx *c, EventPair *out)
+{
+    EventPair ep;
+    LBM_CUDA(c, cudaEventCreate(&ep.start));
+    cudaError_t e = cudaEventCreate(&ep.stop);
+    if (e != cudaSuccess) {
+        cudaEventDestroy(ep.start);
+        return fail(c, LBM_ERR_CUDA, "cudaEventCreate(%d) - %s", (int)e, cudaGetErrorName(e));
+    }
+    *out = ep;
+    return LBM_OK;
+}
+
+// Fold finished event pairs into the accumulator so that very long runs driven by lbm_step do not
+// hold an unbounded number of CUDA events.
+static int fold_events(lbm_ctx *c, bool all)
+{
+    if (!all && c->compute_events.size() < 4096) return LBM_OK;
+    if (!c->compute_events.empty()) LBM_CUDA(c, cudaEventSynchronize(c->compute_events.back().stop));
+    for (auto &e : c->compute_events) {
+        float ms = 0.f;
+        LBM_CUDA(c, cudaEventElapsedTime(&ms, e.start, e.stop));
+        c->kernels_ms_accum += ms;
+        cudaEventDestroy(e.start);
+        cudaEventDestroy(e.stop);
+    }
+    c->compute_events.clear();
+    return LBM_OK;
+}
+
+int lbm_step(lbm_ctx *c, int update_macro)
+{
+    if (!c) return LBM_ERR_INVALID;
+    if (!c->initialised) return fail(c, LBM_ERR_STATE, "lbm_step before lbm_init");
+    int rc = use_device(c);
+    if (rc != LBM_OK) return rc;
+    if ((rc = fold_events(c, false)) != LBM_OK) return rc;
+    EventPair ep;
+    if ((rc = push_pair(c, &ep)) != LBM_OK) return rc;
+    c->compute_events.push_back(ep);
+    LBM_CUDA(c, cudaEventRecord(ep.start, c->stream));
+    LBM_CUDA(c, launch_step(c, c->z_begin, c->z_end, update_macro != 0, c->stream));
+    LBM_CUDA(c, cudaEventRecord(ep.stop, c->stream));
+    c->cur ^= 1;
+    c->iteration += 1;
+    return record_last(c);
+}
+
+int lbm_run(lbm_ctx *c, int n_iterations, int every)
+{
+    if (!c) return LBM_ERR_INVALID;
+    if (!c->initialised) return fail(c, LBM_ERR_STATE, "lbm_run before lbm_init");
+    if (n_iterations < 0 || every < 0) return fail(c, LBM_ERR_INVALID, "lbm_run: negative argument");
+    if (n_iterations == 0) return LBM_OK;
+    int rc = use_device(c);
+    if (rc != LBM_OK) return rc;
+    if ((rc = fold_events(c, false)) != LBM_OK) return rc;
+    EventPair ep;
+    if ((rc = push_pair(c, &ep)) != LBM_OK) return rc;
+    c->compute_events.push_back(ep);
+    LBM_CUDA(c, cudaEventRecord(ep.start, c->stream));
+    for (int i = 0; i < n_iterations; ++i) {
+        const int64_t it = c->iteration + 1;  // 1-based like lbmcl.hpp:435
+        const bool macro = every != 0 && (it % every) == 0;
+        LBM_CUDA(c, launch_step(c, c->z_begin, c->z_end, macro, c->stream));
+        c->cur ^= 1;
+        c->iteration = it;
+    }
+    LBM_CUDA(c, cudaEventRecord(ep.stop, c->stream));
+    return record_last(c);
+}
+
+int lbm_sync(lbm_ctx *c)
+{
+    if (!c) return LBM_ERR_INVALID;
+    int rc = use_device(c);
+    if (rc != LBM_OK) return rc;
+    LBM_CUDA(c, cudaStreamSynchronize(c->stream));
+    return LBM_OK;
+}
+
+int lbm_read_macros(lbm_ctx *c, void *rho_host, void *u_host)
+{
+    if (!c) return LBM_ERR_INVALID;
+    if (!c->initialised) return fail(c, LBM_ERR_STATE, "lbm_read_macros before lbm_init");
+    int rc = use_device(c);
+    if (rc != LBM_OK) return rc;
+    const long long plane = (long long)c->dim * c->dim;
+    const long long n_cube = plane * c->dim;
+    const size_t off_local = (size_t)(c->z_begin - c->zs0) * plane * c->esize;
+    const size_t off_global = (size_t)c->z_begin * plane * c->esize;
+    const size_t bytes = (size_t)(c->z_end - c->z_begin) * plane * c->esize;
+    if (rho_host)
+        LBM_CUDA(c, cudaMemcpyAsync((char *)rho_host + off_global, (const char *)c->rho + off_local, bytes,
+                                    cudaMemcpyDeviceToHost, c->stream));
+    if (u_host)
+        for (int k = 0; k < 3; ++k)
+            LBM_CUDA(c, cudaMemcpyAsync((char *)u_host + (size_t)k * n_cube * c->esize + off_global,
+                                        (const char *)c->u + (size_t)k * c->n_local * c->esize + off_local, bytes,
+                                        cudaMemcpyDeviceToHost, c->stream));
+    if ((rc = record_last(c)) != LBM_OK) return rc;
+    LBM_CUDA(c, cudaStreamSynchronize(c->stream));
+    return LBM_OK;
+}
+
+int lbm_read_map(lbm_ctx *c, int32_t *map_host)
+{
+    if (!c || !map_host) return LBM_ERR_INVALID;
+    int rc = use_device(c);
+    if (rc != LBM_OK) return rc;
+    const long long n_cube = (long long)c->dim * c->dim * c->dim;
+    int *d = nullptr;
+    LBM_CUDA(c, cudaMalloc(&d, (size_t)n_cube * sizeof(int)));
+    const int bx = c->dim < 64 ? c->dim : 64;
+    const int by = (256 / bx) < c->dim ? (256 / bx) : c->dim;
+    map_kernel<<<dim3(c->dim / bx, c->dim / by, c->dim), dim3(bx, by, 1), 0, c->stream>>>(d, c->dim);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(map_host, d, (size_t)n_cube * sizeof(int), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    LBM_CUDA(c, e);
+    return record_last(c);
+}
+
+int lbm_read_f(lbm_ctx *c, void *f_host)
+{
+    if (!c || !f_host) return LBM_ERR_INVALID;
+    if (!c->initialised) return fail(c, LBM_ERR_STATE, "lbm_read_f before lbm_init");
+    if (c->z_begin != 0 || c->z_end != c->dim)
+        return fail(c, LBM_ERR_INVALID, "lbm_read_f: only on a context that owns the whole cube");
+    int rc = use_device(c);
+    if (rc != LBM_OK) return rc;
+    const long long n_cube = (long long)c->dim * c->dim * c->dim;
+    const size_t bytes = (size_t)n_cube * Q * c->esize;
+    void *d = nullptr;
+    LBM_CUDA(c, cudaMalloc(&d, bytes));
+    const int bx = c->dim < 64 ? c->dim : 64;
+    const int by = (256 / bx) < c->dim ? (256 / bx) : c->dim;
+    const dim3 b(bx, by, 1), g(c->dim / bx, c->dim / by, c->dim);
+    const int pristine = c->iteration == 0 ? 1 : 0;
+    if (c->p.precision == LBM_F32)
+        reference_view_kernel<float><<<g, b, 0, c->stream>>>((const float *)c->f[c->cur], (float *)d, c->dim, c->zs0,
+                                                             c->nz_local, 0, c->dim, c->lay, c->lay, c->cf, pristine);
+    else
+        reference_view_kernel<double><<<g, b, 0, c->stream>>>((const double *)c->f[c->cur], (double *)d, c->dim,
+                                                              c->zs0, c->nz_local, 0, c->dim, c->lay, c->lay, c->cd,
+                                                              pristine);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(f_host, d, bytes, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    LBM_CUDA(c, e);
+    return record_last(c);
+}
+
+int lbm_time_ms(lbm_ctx *c, double *total_ms, double *kernels_ms)
+{
+    if (!c) return LBM_ERR_INVALID;
+    if (!c->initialised) return fail(c, LBM_ERR_STATE, "lbm_time_ms before lbm_init");
+    int rc = use_device(c);
+    if (rc != LBM_OK) return rc;
+    LBM_CUDA(c, cudaStreamSynchronize(c->stream));
+    LBM_CUDA(c, cudaEventSynchronize(c->ev_last));
+    if (total_ms) {
+        float ms = 0.f;
+        LBM_CUDA(c, cudaEventElapsedTime(&ms, c->ev_init_start, c->ev_last));
+        *total_ms = ms;
+    }
+    if (kernels_ms) {
+        if ((rc = fold_events(c, true)) != LBM_OK) return rc;
+        *kernels_ms = c->kernels_ms_accum;
+    }
+    return LBM_OK;
+}
+
+int lbm_device_name(const lbm_ctx *c, char *buf, size_t buflen)
+{
+    if (!c || !buf || buflen == 0) return LBM_ERR_INVALID;
+    snprintf(buf, buflen, "%s", c->device_name.c_str());
+    return LBM_OK;
+}
+
+int lbm_effective_params(const lbm_ctx *c, double out[3])
+{
+    if (!c || !out) return LBM_ERR_INVALID;
+    out[0] = c->eff_viscosity;
+    out[1] = c->eff_velocity;
+    out[2] = c->eff_inv_tau;
+    return LBM_OK;
+}
+
+int lbm_block_shape(const lbm_ctx *c, int32_t block[3], int32_t *cells_per_thread)
+{
+    if (!c) return LBM_ERR_INVALID;
+    if (block) {
+        block[0] = (int32_t)c->block.x;
+        block[1] = (int32_t)c->block.y;
+        block[2] = (int32_t)c->block.z;
+    }
+    if (cells_per_thread) *cells_per_thread = c->vec;
+    return LBM_OK;
+}
+
+int64_t lbm_device_bytes(const lbm_ctx *c) { return c ? c->device_bytes : 0; }
+int64_t lbm_launch_count(const lbm_ctx *c) { return c ? c->launches : 0; }
+int64_t lbm_iteration(const lbm_ctx *c) { return c ? c->iteration : 0; }
+
+int lbm_set_stream(lbm_ctx *c, void *cuda_stream)
+{
+    if (!c) return LBM_ERR_INVALID;
+    c->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->own_stream;
+    return LBM_OK;
+}
+
+// ---- dense halo transport (one process per device) ----
+
+int64_t lbm_halo_elems(const lbm_ctx *c) { return c ? (int64_t)5 * c->dim * c->dim : 0; }
+void *lbm_halo_send_buffer(lbm_ctx *c, int face) { return (c && (face == 0 || face == 1)) ? c->halo_send[face] : nullptr; }
+void *lbm_halo_recv_buffer(lbm_ctx *c, int face) { return (c && (face == 0 || face == 1)) ? c->halo_recv[face] : nullptr; }
+
+}  // extern "C"
+
+template <typename T, bool PACK>
+static cudaError_t halo_launch(lbm_ctx *c, void *lattice, void *dense, long long plane_local, int dir_up)
+{
+    const int bx = c->dim < 256 ? c->dim : 256;
+    const dim3 b(bx, 1, 1), g(c->dim / bx, c->dim, 5);
+    halo_kernel<T, PACK><<<g, b, 0, c->stream>>>((T *)lattice, (T *)dense, c->dim, plane_local, c->lay, dir_up);
+    return cudaGetLastError();
+}
+
+extern "C" {
+
+// Packs, from the lattice the NEXT iteration reads (i.e. the one just written), what the neighbours
+// will gather: low face -> populations with e_z = -1 of plane z_begin; high face -> e_z = +1 of plane
+// z_end - 1.
+int lbm_halo_pack(lbm_ctx *c)
+{
+    if (!c) return LBM_ERR_INVALID;
+    int rc = use_device(c);
+    if (rc != LBM_OK) return rc;
+    void *lat = c->f[c->cur];
+    const bool f32 = c->p.precision == LBM_F32;
+    if (c->halo_send[0]) {
+        const long long pl = c->z_begin - c->zs0;
+        LBM_CUDA(c, f32 ? halo_launch<float, true>(c, lat, c->halo_send[0], pl, 0)
+                        : halo_launch<double, true>(c, lat, c->halo_send[0], pl, 0));
+    }
+    if (c->halo_send[1]) {
+        const long long pl = (c->z_end - 1) - c->zs0;
+        LBM_CUDA(c, f32 ? halo_launch<float, true>(c, lat, c->halo_send[1], pl, 1)
+                        : halo_launch<double, true>(c, lat, c->halo_send[1], pl, 1));
+    }
+    return LBM_OK;
+}
+
+// Scatters what the neighbours packed into the halo planes of the lattice the NEXT iteration reads:
+// low halo plane (z_begin - 1) receives e_z = +1 populations, high halo plane (z_end) e_z = -1.
+int lbm_halo_unpack(lbm_ctx *c)
+{
+    if (!c) return LBM_ERR_INVALID;
+    int rc = use_device(c);
+    if (rc != LBM_OK) return rc;
+    void *lat = c->f[c->cur];
+    const bool f32 = c->p.precision == LBM_F32;
+    if (c->halo_recv[0]) {
+        const long long pl = (c->z_begin - 1) - c->zs0;
+        LBM_CUDA(c, f32 ? halo_launch<float, false>(c, lat, c->halo_recv[0], pl, 1)
+                        : halo_launch<double, false>(c, lat, c->halo_recv[0], pl, 1));
+    }
+    if (c->halo_recv[1]) {
+        const long long pl = c->z_end - c->zs0;
+        LBM_CUDA(c, f32 ? halo_launch<float, false>(c, lat, c->halo_recv[1], pl, 0)
+                        : halo_launch<double, false>(c, lat, c->halo_recv[1], pl, 0));
+    }
+    return LBM_OK;
+}
+
+}  // extern "C"
+
+#include "lbm_group.inl"

@@ -1,0 +1,434 @@
+// sm_100a kernels of the D3Q19 BGK collide-and-stream path.
+//
+// What the reference computes per iteration (kernels.cl:321-425, a PUSH scheme): read the 19
+// pre-collision populations of a cell, lid pre-fix, rho/u, optional macro store, lid equilibrium or
+// in-node bounce-back swap, BGK, scatter to the 19 neighbours of the other lattice.
+//
+// What these kernels do instead (two-lattice PULL scheme, post-collision storage):
+//
+//   G_k(c, q)  = value that iteration k leaves in cell c for direction q and that iteration k+1 of
+//                cell c + e_q will gather           (the reference's S_k(c + e_q, q))
+//
+//   iteration:  f_q = G_{k-1}(c - e_q, q)  ->  BC / collide exactly as the reference  ->  G_k(c, q)
+//
+// so that every load and every store of a thread is an aligned, x-contiguous vector (VEC cells per
+// thread); the +-1 shifts in x are done with warp shuffles, and only the first/last lane of a row
+// segment issues one extra scalar load.  Cell types come from the coordinates (0 B/cell, SURVEY
+// F12) instead of the reference's `map` buffer.
+//
+// Ghost values.  In the reference a slot (c, q) whose source c - e_q is a WALL cell is never written
+// and keeps its `initialize` value for ever.  Here
+//   * wall ROWS (y or z on 0 / DIM-1) are never written by the step kernel, and `init_kernel` leaves
+//     in them exactly those constants (G_0(c, q) = initial equilibrium of the destination c + e_q), so
+//     that gathering from them needs no special case;
+//   * wall cells INSIDE a row (x = 0, DIM-1) are overwritten by the vector stores with don't-care
+//     values; the populations that cells x = 1 / x = DIM-2 would gather from them are replaced by the
+//     same constants from StepArgs::stale.
+//
+// Algorithmic traffic: 19 loads + 19 stores per cell = 152 B (fp32) / 304 B (fp64); nothing else is
+// read.  Macro stores (4 values per cell) happen only on iterations flagged by `every`.
+#pragma once
+
+#include "lbm_d3q19.cuh"
+
+namespace lbm {
+
+template <typename T, int N>
+struct alignas(sizeof(T) * N) Pack {
+    T v[N];
+};
+
+template <typename T>
+struct StepArgs {
+    T *__restrict__ dst;        // lattice written by this iteration      (G_k)
+    const T *__restrict__ src;  // lattice gathered from                  (G_{k-1})
+    T *__restrict__ rho;        // [n_local]
+    T *__restrict__ u;          // [3][n_local]
+    // same-process z-slab neighbours: where the crossing populations of the first / last owned plane
+    // are ALSO stored (the neighbour's halo plane of the lattice it reads next), or nullptr
+    T *__restrict__ peer_lo;    // receives q with e_z = -1 of plane z_own_begin
+    T *__restrict__ peer_hi;    // receives q with e_z = +1 of plane z_own_end - 1
+    long long peer_lo_plane;    // local plane index of that halo plane in the neighbour's storage
+    long long peer_hi_plane;
+    int z_own_begin, z_own_end; // owned global planes of this slab
+    int dim;
+    int zs0;                    // global z of local plane 0
+    int z_begin, z_end;         // global planes [z_begin, z_end) computed by this launch
+    long long n_local;          // cells in local storage (pitch of the u components)
+    Layout lay;
+    Consts<T> c;
+    T stale[2][Q];              // [0]: w_q (rest equilibrium); [1]: f_eq_q(1, (U,0,0)); see header
+};
+
+template <typename T>
+struct InitArgs {
+    T *__restrict__ f0;
+    T *__restrict__ f1;
+    T *__restrict__ rho;
+    T *__restrict__ u;
+    int dim;
+    int zs0;
+    int nz_local;               // stored planes
+    long long n_local;
+    Layout lay;
+    Consts<T> c;
+};
+
+// Initial equilibrium f_eq_q(1, (ux, 0, 0)) with the reference's operation order (kernels.cl:303-309);
+// always strict: initial values are not subject to -o in any observable way except through rounding,
+// and a single definition keeps the ghost constants identical everywhere.
+template <typename T, int q>
+__device__ __forceinline__ T init_feq(const Consts<T> &c, T ux)
+{
+    using A = Arith<T, false>;
+    const T u2 = A::add(A::add(A::mul(ux, ux), T(0)), T(0));
+    const T eu = e_dot_u<A, q>(ux, T(0), T(0));
+    return A::mul(A::mul(T(1), c.w[wclass(q)]), eq_poly<A>(eu, A::mul(T(1.5), u2)));
+}
+
+// `initialize` (kernels.cl:277-318) for the pull representation: one thread per stored cell.
+//   rho/u : 1 and (U or 0, 0, 0) on FLUID / MOVING cells, NaN elsewhere (kernels.cl:297-300)
+//   both lattices: G_0(c, q) = f_eq_q(1, u0(c + e_q)), i.e. the initial state already "pre-streamed",
+//   so that the first iteration gathers exactly the reference's analytic S_0.
+template <typename T>
+__global__ void __launch_bounds__(256) init_kernel(const InitArgs<T> a)
+{
+    const int dim = a.dim;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int zl = blockIdx.z * blockDim.z + threadIdx.z;
+    if (x >= dim || y >= dim || zl >= a.nz_local) return;
+    const int z = a.zs0 + zl;
+    const long long id = x + (long long)y * dim + (long long)zl * dim * dim;
+
+    const int t = cell_type(x, y, z, dim);
+    const bool keep = is_collision(t);
+    const T nan = static_cast<T>(__int_as_float(0x7fc00000));
+    const T ux0 = has_front_bit(x, y, z, dim) ? a.c.u_lid : T(0);
+    a.rho[id] = keep ? T(1) : nan;
+    a.u[id] = keep ? ux0 : nan;
+    a.u[a.n_local + id] = keep ? T(0) : nan;
+    a.u[2 * a.n_local + id] = keep ? T(0) : nan;
+
+    const long long b = a.lay.base(id);
+    const long long qp = a.lay.qpitch();
+    static_for<Q>([&](auto qc) {
+        constexpr int q = decltype(qc)::value;
+        const bool front = has_front_bit(x + ex(q), y + ey(q), z + ez(q), dim);
+        const T v = init_feq<T, q>(a.c, front ? a.c.u_lid : T(0));
+        a.f0[b + q * qp] = v;
+        a.f1[b + q * qp] = v;
+    });
+}
+
+// The two ghost-constant tables of StepArgs::stale, computed on the device with the same code as
+// init_kernel so that they are bit-identical to what the lattices hold.
+template <typename T>
+__global__ void stale_kernel(Consts<T> c, T *out /* [2][Q] */)
+{
+    static_for<Q>([&](auto qc) {
+        constexpr int q = decltype(qc)::value;
+        out[q] = init_feq<T, q>(c, T(0));
+        out[Q + q] = init_feq<T, q>(c, c.u_lid);
+    });
+}
+
+// BGK relaxation of one cell, kernels.cl:355-380 and :412-418 (fluid cells).
+template <typename T, bool FAST>
+__device__ __forceinline__ void collide_fluid(T (&f)[Q], const Consts<T> &c, T &rho, T &ux, T &uy, T &uz)
+{
+    using A = Arith<T, FAST>;
+    // kernels.cl:355 — left-to-right sum
+    rho = f[0];
+#pragma unroll
+    for (int q = 1; q < Q; ++q) rho = A::add(rho, f[q]);
+    // kernels.cl:376-378
+    const T px = A::add(A::add(A::add(A::add(f[1], f[7]), f[10]), f[11]), f[15]);
+    const T mx = A::add(A::add(A::add(A::add(f[3], f[8]), f[9]), f[13]), f[17]);
+    const T py = A::add(A::add(A::add(A::add(f[2], f[7]), f[8]), f[12]), f[16]);
+    const T my = A::add(A::add(A::add(A::add(f[4], f[9]), f[10]), f[14]), f[18]);
+    const T pz = A::add(A::add(A::add(A::add(f[6], f[15]), f[16]), f[17]), f[18]);
+    const T mz = A::add(A::add(A::add(A::add(f[5], f[11]), f[12]), f[13]), f[14]);
+    ux = A::div(A::sub(px, mx), rho);
+    uy = A::div(A::sub(py, my), rho);
+    uz = A::div(A::sub(pz, mz), rho);
+    // kernels.cl:390
+    const T u2 = A::add(A::add(A::mul(ux, ux), A::mul(uy, uy)), A::mul(uz, uz));
+    const T c15u2 = A::mul(T(1.5), u2);
+    const T rw[3] = { A::mul(rho, c.w[0]), A::mul(rho, c.w[1]), A::mul(rho, c.w[2]) };
+    // kernels.cl:412-418 with compute_bgk (kernels.cl:270-273): f + INV_TAU * (feq - f)
+    static_for<Q>([&](auto qc) {
+        constexpr int q = decltype(qc)::value;
+        const T eu = e_dot_u<A, q>(ux, uy, uz);
+        const T feq = A::mul(rw[wclass(q)], eq_poly<A>(eu, c15u2));
+        f[q] = A::add(f[q], A::mul(c.inv_tau, A::sub(feq, f[q])));
+    });
+}
+
+// Moving-lid cell, kernels.cl:343-349, :362-366, :393-398, :412-418.  rho comes from the gathered
+// populations with the five wall-side ones replaced by their opposites; u is forced to (U,0,0); all
+// 19 populations become f_eq(rho, u).  The BGK step that follows in the reference acts on an exact
+// equilibrium: feq - f == +0, INV_TAU * 0 == 0, f + 0 == f, so it is the identity and is not issued.
+template <typename T, bool FAST>
+__device__ __forceinline__ void collide_lid(T (&f)[Q], const Consts<T> &c, T &rho)
+{
+    using A = Arith<T, FAST>;
+    f[5] = f[opp(5)];
+    f[11] = f[opp(11)];
+    f[12] = f[opp(12)];
+    f[13] = f[opp(13)];
+    f[14] = f[opp(14)];
+    rho = f[0];
+#pragma unroll
+    for (int q = 1; q < Q; ++q) rho = A::add(rho, f[q]);
+    const T U = c.u_lid;
+    const T c15u2 = A::mul(T(1.5), A::mul(U, U));  // (U*U + 0*0) + 0*0 == U*U exactly
+    const T rw[3] = { A::mul(rho, c.w[0]), A::mul(rho, c.w[1]), A::mul(rho, c.w[2]) };
+    static_for<Q>([&](auto qc) {
+        constexpr int q = decltype(qc)::value;
+        const T eu = e_dot_u<A, q>(U, T(0), T(0));
+        f[q] = A::mul(rw[wclass(q)], eq_poly<A>(eu, c15u2));
+    });
+}
+
+// In-node full-way bounce-back, kernels.cl:400-408: swap the nine opposite pairs, no collision.
+template <typename T>
+__device__ __forceinline__ void bounce_back(T (&f)[Q])
+{
+    static_for<Q>([&](auto qc) {
+        constexpr int q = decltype(qc)::value;
+        if constexpr (q < opp(q)) {
+            const T tmp = f[q];
+            f[q] = f[opp(q)];
+            f[opp(q)] = tmp;
+        }
+    });
+}
+
+// One iteration.  Thread (tx, ty, tz) of block (bx, by, bz) owns the VEC cells
+//   x0 .. x0+VEC-1 = (blockIdx.x*bx + tx)*VEC .. ,  y = blockIdx.y*by + ty,  z = z_begin + blockIdx.z*bz + tz.
+// Requirements (checked by the host): bx a power of two, bx*VEC divides DIM, by divides DIM,
+// VEC divides stride (so every vector is aligned and inside one CSoA run).
+template <typename T, int VEC, bool FAST, bool MACRO, bool PEER>
+__global__ void __launch_bounds__(256) step_pull_kernel(const StepArgs<T> a)
+{
+    using V = Pack<T, VEC>;
+    const int dim = a.dim;
+    const int tx = threadIdx.x;
+    const int x0 = (blockIdx.x * blockDim.x + tx) * VEC;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int z = a.z_begin + blockIdx.z * blockDim.z + threadIdx.z;
+
+    const int rowbits = (z < a.z_end) ? row_bits(y, z, dim) : CT_WALL;
+    const bool live = rowbits != CT_WALL;  // wall rows: never read, never written
+    const unsigned mask = __ballot_sync(0xffffffffu, live);
+    if (!live) return;
+
+    const long long plane = (long long)dim * dim;
+    const long long id0 = x0 + (long long)y * dim + (long long)(z - a.zs0) * plane;
+    const long long qp = a.lay.qpitch();
+
+    // ---- gather: f[q][j] = G(x0 + j - ex, y - ey, z - ez, q) ----
+    T f[Q][VEC];
+    if constexpr (VEC == 1) {
+        static_for<Q>([&](auto qc) {
+            constexpr int q = decltype(qc)::value;
+            const long long sid = id0 - ex(q) - (long long)ey(q) * dim - (long long)ez(q) * plane;
+            f[q][0] = a.src[a.lay.base(sid) + q * qp];
+        });
+    } else {
+        // lanes of one row segment are consecutive lanes of the warp
+        const int seg = blockDim.x < 32 ? blockDim.x : 32;
+        const bool seg_first = (tx & (seg - 1)) == 0;
+        const bool seg_last = (tx & (seg - 1)) == seg - 1;
+        static_for<Q>([&](auto qc) {
+            constexpr int q = decltype(qc)::value;
+            const long long sid = id0 - (long long)ey(q) * dim - (long long)ez(q) * plane;
+            const T *p = a.src + q * qp;
+            const V v = *reinterpret_cast<const V *>(p + a.lay.base(sid));
+            if constexpr (ex(q) == 0) {
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) f[q][j] = v.v[j];
+            } else if constexpr (ex(q) == 1) {
+                T e = __shfl_up_sync(mask, v.v[VEC - 1], 1);
+                if (seg_first) e = (x0 > 0) ? p[a.lay.base(sid - 1)] : T(0);
+                f[q][0] = e;
+#pragma unroll
+                for (int j = 1; j < VEC; ++j) f[q][j] = v.v[j - 1];
+            } else {
+                T e = __shfl_down_sync(mask, v.v[0], 1);
+                if (seg_last) e = (x0 + VEC < dim) ? p[a.lay.base(sid + VEC)] : T(0);
+                f[q][VEC - 1] = e;
+#pragma unroll
+                for (int j = 0; j < VEC - 1; ++j) f[q][j] = v.v[j + 1];
+            }
+        });
+    }
+
+    // ---- ghost constants for what cells x = 1 / x = DIM-2 would gather from the x walls ----
+    {
+        const int lid = (rowbits & CT_FRONT) ? 1 : 0;  // the gathering cell started with u = (U,0,0)
+        constexpr int JL = VEC >= 2 ? 1 : 0;           // x == 1     is element JL of the thread at x0 == XL
+        constexpr int XL = VEC >= 2 ? 0 : 1;
+        constexpr int JR = VEC >= 2 ? VEC - 2 : 0;     // x == DIM-2 is element JR of the thread at x0 == DIM-XR
+        constexpr int XR = VEC >= 2 ? VEC : 2;
+        if (x0 == XL) {
+            static_for<Q>([&](auto qc) {
+                constexpr int q = decltype(qc)::value;
+                if constexpr (ex(q) == 1) f[q][JL] = a.stale[lid][q];
+            });
+        }
+        if (x0 == dim - XR) {
+            static_for<Q>([&](auto qc) {
+                constexpr int q = decltype(qc)::value;
+                if constexpr (ex(q) == -1) f[q][JR] = a.stale[lid][q];
+            });
+        }
+    }
+
+    // ---- boundary conditions + collision, cell by cell ----
+    const T nan = static_cast<T>(__int_as_float(0x7fc00000));
+    T m_rho[VEC], m_ux[VEC], m_uy[VEC], m_uz[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+        const int t = cell_type_from_row(rowbits, x0 + j, dim);
+        T fc[Q];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) fc[q] = f[q][j];
+        T rho = nan, ux = nan, uy = nan, uz = nan;
+        if (t == CT_FLUID) {
+            collide_fluid<T, FAST>(fc, a.c, rho, ux, uy, uz);
+        } else if (t & CT_MOVING) {
+            collide_lid<T, FAST>(fc, a.c, rho);
+            ux = a.c.u_lid;
+            uy = T(0);
+            uz = T(0);
+        } else if (is_bounceback(t)) {
+            bounce_back<T>(fc);
+        }  // CORNER: pass-through; WALL (x = 0, DIM-1): don't care
+#pragma unroll
+        for (int q = 0; q < Q; ++q) f[q][j] = fc[q];
+        m_rho[j] = rho;
+        m_ux[j] = ux;
+        m_uy[j] = uy;
+        m_uz[j] = uz;
+    }
+
+    // ---- store G_k ----
+    const long long b0 = a.lay.base(id0);
+    static_for<Q>([&](auto qc) {
+        constexpr int q = decltype(qc)::value;
+        V v;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) v.v[j] = f[q][j];
+        *reinterpret_cast<V *>(a.dst + b0 + q * qp) = v;
+        if constexpr (PEER) {
+            // fused halo exchange: the five populations that cross the slab face also go straight
+            // into the neighbour's halo plane (NVLink stores when the neighbour is a peer device)
+            if constexpr (ez(q) == -1) {
+                if (a.peer_lo != nullptr && z == a.z_own_begin) {
+                    const long long pid = x0 + (long long)y * dim + a.peer_lo_plane * plane;
+                    *reinterpret_cast<V *>(a.peer_lo + a.lay.base(pid) + q * qp) = v;
+                }
+            } else if constexpr (ez(q) == 1) {
+                if (a.peer_hi != nullptr && z == a.z_own_end - 1) {
+                    const long long pid = x0 + (long long)y * dim + a.peer_hi_plane * plane;
+                    *reinterpret_cast<V *>(a.peer_hi + a.lay.base(pid) + q * qp) = v;
+                }
+            }
+        }
+    });
+
+    // ---- macro store (kernels.cl:383-388): only FLUID / MOVING cells; the others keep their NaN ----
+    if constexpr (MACRO) {
+        const bool row_stores = !(rowbits & (CT_TOP | CT_BOTTOM | CT_BACK));
+        if (row_stores) {
+            V r, vx, vy, vz;
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                r.v[j] = m_rho[j];
+                vx.v[j] = m_ux[j];
+                vy.v[j] = m_uy[j];
+                vz.v[j] = m_uz[j];
+            }
+            *reinterpret_cast<V *>(a.rho + id0) = r;
+            *reinterpret_cast<V *>(a.u + id0) = vx;
+            *reinterpret_cast<V *>(a.u + a.n_local + id0) = vy;
+            *reinterpret_cast<V *>(a.u + 2 * a.n_local + id0) = vz;
+        }
+    }
+}
+
+// Cell-type map (kernels.cl:290), only for the -m dump.
+__global__ void map_kernel(int *__restrict__ map, int dim)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int z = blockIdx.z;
+    if (x >= dim || y >= dim) return;
+    map[x + (long long)y * dim + (long long)z * dim * dim] = cell_type(x, y, z, dim);
+}
+
+// Reference view of the lattice the next iteration reads (for the -f dump, lbmcl.hpp:206-258):
+//   S(c, q) = G(c - e_q, q)        if c - e_q is inside the cube and not WALL   (a pushed value)
+//           = NaN                  else if c is WALL                            (kernels.cl:311-317)
+//           = f_eq_q(1, u0(c))     otherwise                                    (never-written slot)
+// `pristine` (no iteration executed yet): WALL cells are all NaN because nothing has been pushed.
+// Output in the reference's CSoA(stride) order over the owned planes, global cell ids.
+template <typename T>
+__global__ void __launch_bounds__(256) reference_view_kernel(const T *__restrict__ g, T *__restrict__ out,
+                                                             int dim, int zs0, int nz_local, int z_begin,
+                                                             int z_end, Layout lay_local, Layout lay_global,
+                                                             Consts<T> c, int pristine)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int z = z_begin + blockIdx.z * blockDim.z + threadIdx.z;
+    if (x >= dim || y >= dim || z >= z_end) return;
+    const long long plane = (long long)dim * dim;
+    const long long gid = x + (long long)y * dim + (long long)z * plane;
+    const int t = cell_type(x, y, z, dim);
+    const T nan = static_cast<T>(__int_as_float(0x7fc00000));
+    const T ux0 = has_front_bit(x, y, z, dim) ? c.u_lid : T(0);
+    static_for<Q>([&](auto qc) {
+        constexpr int q = decltype(qc)::value;
+        const int sx = x - ex(q), sy = y - ey(q), sz = z - ez(q);
+        const bool inside = sx >= 0 && sx < dim && sy >= 0 && sy < dim && sz >= 0 && sz < dim;
+        T v;
+        if (inside && cell_type(sx, sy, sz, dim) != CT_WALL && !(pristine && t == CT_WALL)) {
+            const int szl = sz - zs0;  // source plane must be stored locally (owned or halo)
+            const long long sid = sx + (long long)sy * dim + (long long)szl * plane;
+            v = (szl >= 0 && szl < nz_local) ? g[lay_local.base(sid) + q * lay_local.qpitch()] : nan;
+        } else if (t == CT_WALL) {
+            v = nan;
+        } else {
+            v = init_feq<T, q>(c, ux0);
+        }
+        out[lay_global.base(gid) + q * lay_global.qpitch()] = v;
+    });
+}
+
+// Dense halo transport for the one-process-per-device mode.  A packed halo is [5][DIM][DIM]
+// (population slot, y, x).  kDown / kUp list the crossing populations.
+__device__ __constant__ const int kDown[5] = { 5, 11, 12, 13, 14 };   // e_z = -1
+__device__ __constant__ const int kUp[5] = { 6, 15, 16, 17, 18 };     // e_z = +1
+
+// dir_up != 0: populations with e_z = +1; plane_local: plane of the local storage to read / write
+template <typename T, bool PACK>
+__global__ void __launch_bounds__(256) halo_kernel(T *__restrict__ lattice, T *__restrict__ dense, int dim,
+                                                   long long plane_local, Layout lay, int dir_up)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    const int s = blockIdx.z;
+    if (x >= dim) return;
+    const int q = dir_up ? kUp[s] : kDown[s];
+    const long long plane = (long long)dim * dim;
+    const long long id = x + (long long)y * dim + plane_local * plane;
+    const long long li = lay.base(id) + q * lay.qpitch();
+    const long long di = x + (long long)y * dim + (long long)s * plane;
+    if (PACK) dense[di] = lattice[li];
+    else lattice[li] = dense[di];
+}
+
+}  // namespace lbm
