@@ -173,6 +173,16 @@ int lbm_set_stream(lbm_ctx *ctx, void *cuda_stream);
 
 typedef enum lbm_face { LBM_FACE_LOW = 0, LBM_FACE_HIGH = 1 } lbm_face;
 
+/* Split-phase iteration for hosts that overlap the halo exchange themselves: launch the compute
+ * kernel over the owned global planes [z_begin, z_end) only, on the context's current stream
+ * (lbm_set_stream), without advancing the iteration; lbm_advance() then swaps the two lattices and
+ * increments the iteration counter (host-side bookkeeping only).  One iteration = every owned plane
+ * covered exactly once by lbm_step_planes calls, then one lbm_advance. */
+int lbm_step_planes(lbm_ctx *ctx, int z_begin, int z_end, int update_macro);
+int lbm_advance(lbm_ctx *ctx);
+/* owned plane range of the context */
+int lbm_z_range(const lbm_ctx *ctx, int32_t *z_begin, int32_t *z_end);
+
 /* number of elements (not bytes) in one packed halo: 5 * DIM * DIM */
 int64_t lbm_halo_elems(const lbm_ctx *ctx);
 /* device pointers of the dense halo buffers; NULL for a face on the cube boundary */

@@ -23,7 +23,7 @@ EXPORTS = [
     "lbm_default_params", "lbm_create", "lbm_destroy", "lbm_last_error", "lbm_init", "lbm_step", "lbm_run",
     "lbm_sync", "lbm_read_macros", "lbm_read_map", "lbm_read_f", "lbm_time_ms", "lbm_device_name",
     "lbm_effective_params", "lbm_block_shape", "lbm_device_bytes", "lbm_launch_count", "lbm_iteration",
-    "lbm_set_stream", "lbm_halo_elems", "lbm_halo_send_buffer", "lbm_halo_recv_buffer", "lbm_halo_pack",
+    "lbm_set_stream", "lbm_step_planes", "lbm_advance", "lbm_z_range", "lbm_halo_elems", "lbm_halo_send_buffer", "lbm_halo_recv_buffer", "lbm_halo_pack",
     "lbm_halo_unpack", "lbm_group_create", "lbm_group_destroy", "lbm_group_last_error", "lbm_group_size",
     "lbm_group_ctx", "lbm_group_init", "lbm_group_run", "lbm_group_sync", "lbm_group_read_macros",
     "lbm_group_time_ms",
@@ -95,6 +95,9 @@ def load() -> ctypes.CDLL:
     lib.lbm_iteration.argtypes = [vp]
     lib.lbm_iteration.restype = i64
     lib.lbm_set_stream.argtypes = [vp, vp]
+    lib.lbm_step_planes.argtypes = [vp, ci, ci, ci]
+    lib.lbm_advance.argtypes = [vp]
+    lib.lbm_z_range.argtypes = [vp, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]
     lib.lbm_halo_elems.argtypes = [vp]
     lib.lbm_halo_elems.restype = i64
     lib.lbm_halo_send_buffer.argtypes = [vp, ci]
@@ -254,7 +257,19 @@ class Simulation:
     def iteration(self) -> int:
         return self.lib.lbm_iteration(self.h)
 
-    # -- dense halo transport (one process per device) --
+    # -- split-phase iteration + dense halo transport (one process per device) --
+    def step_planes(self, z_begin: int, z_end: int, update_macro: bool = False):
+        self._check(self.lib.lbm_step_planes(self.h, z_begin, z_end, 1 if update_macro else 0))
+
+    def advance(self):
+        self._check(self.lib.lbm_advance(self.h))
+
+    @property
+    def z_range(self):
+        a, b = ctypes.c_int32(), ctypes.c_int32()
+        self._check(self.lib.lbm_z_range(self.h, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
     @property
     def halo_elems(self) -> int:
         return self.lib.lbm_halo_elems(self.h)

@@ -45,6 +45,7 @@ struct lbm_ctx {
     long long n_local = 0;       // stored cells
     long long n_alloc = 0;       // stored cells rounded up to a multiple of the stride
     Layout lay{};
+    int layout_mode = LM_GENERIC;
     int vec = 1;
     dim3 block{1, 1, 1};
     size_t esize = 4;
@@ -189,6 +190,14 @@ StepArgs<T> make_step_args(lbm_ctx *c, int z_begin, int z_end, const Consts<T> &
     a.c = k;
     for (int i = 0; i < 2; ++i)
         for (int q = 0; q < Q; ++q) a.stale[i][q] = stale[i][q];
+    const long long S = c->lay.qpitch(), dim = c->dim, plane = dim * dim, es = (long long)sizeof(T);
+    for (int q = 0; q < Q; ++q) {
+        a.soff[q] = q * S * es;
+        const long long dcell = (long long)ey(q) * dim + (long long)ez(q) * plane;  // cells between the two rows
+        if (c->layout_mode == LM_ROWS) a.goff[q] = (q * S - Q * dcell) * es;
+        else if (c->layout_mode == LM_SOA) a.goff[q] = (q * S - dcell) * es;
+        else a.goff[q] = 0;
+    }
     return a;
 }
 
@@ -200,7 +209,13 @@ cudaError_t launch_step_t(lbm_ctx *c, const StepArgs<T> &a, bool macro, bool pee
     const dim3 b = c->block;
     const dim3 g((unsigned)(c->dim / (b.x * VEC)), (unsigned)(c->dim / b.y), (unsigned)((nz + b.z - 1) / b.z));
     const bool fast = c->p.fast_math != 0;
-#define LBM_LAUNCH(F, M, P) step_pull_kernel<T, VEC, F, M, P><<<g, b, 0, s>>>(a)
+#define LBM_LAUNCH_LM(F, M, P)                                                                   \
+    do {                                                                                          \
+        if (c->layout_mode == LM_ROWS) step_pull_kernel<T, VEC, F, M, P, LM_ROWS><<<g, b, 0, s>>>(a);     \
+        else if (c->layout_mode == LM_SOA) step_pull_kernel<T, VEC, F, M, P, LM_SOA><<<g, b, 0, s>>>(a);  \
+        else step_pull_kernel<T, VEC, F, M, P, LM_GENERIC><<<g, b, 0, s>>>(a);                    \
+    } while (0)
+#define LBM_LAUNCH(F, M, P) LBM_LAUNCH_LM(F, M, P)
     if (peer) {
         if (fast) { if (macro) LBM_LAUNCH(true, true, true); else LBM_LAUNCH(true, false, true); }
         else      { if (macro) LBM_LAUNCH(false, true, true); else LBM_LAUNCH(false, false, true); }
@@ -209,6 +224,7 @@ cudaError_t launch_step_t(lbm_ctx *c, const StepArgs<T> &a, bool macro, bool pee
         else      { if (macro) LBM_LAUNCH(false, true, false); else LBM_LAUNCH(false, false, false); }
     }
 #undef LBM_LAUNCH
+#undef LBM_LAUNCH_LM
     c->launches += 1;
     return cudaGetLastError();
 }
@@ -421,6 +437,10 @@ int lbm_create(const lbm_params *p, lbm_ctx **out)
     c->lay.smod = p->stride - 1;
     c->n_alloc = ((c->n_local + p->stride - 1) / p->stride) * p->stride;
     c->esize = p->precision == LBM_F32 ? 4 : 8;
+    if (p->stride <= p->dim) c->layout_mode = LM_ROWS;
+    else if (p->stride >= c->n_alloc) c->layout_mode = LM_SOA;
+    else c->layout_mode = LM_GENERIC;
+    if (p->reserved[0] == 1) c->layout_mode = LM_GENERIC;  // test hook: force the generic addressing
 
     // widest vector the stride, the row length and the precision allow (16-byte accesses)
     const int vmax = p->precision == LBM_F32 ? 4 : 2;
@@ -713,6 +733,36 @@ int lbm_set_stream(lbm_ctx *c, void *cuda_stream)
 {
     if (!c) return LBM_ERR_INVALID;
     c->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->own_stream;
+    return LBM_OK;
+}
+
+int lbm_step_planes(lbm_ctx *c, int z_begin, int z_end, int update_macro)
+{
+    if (!c) return LBM_ERR_INVALID;
+    if (!c->initialised) return fail(c, LBM_ERR_STATE, "lbm_step_planes before lbm_init");
+    if (z_begin < c->z_begin || z_end > c->z_end || z_begin > z_end)
+        return fail(c, LBM_ERR_INVALID, "lbm_step_planes: [%d, %d) outside the owned planes [%d, %d)", z_begin,
+                    z_end, c->z_begin, c->z_end);
+    int rc = use_device(c);
+    if (rc != LBM_OK) return rc;
+    LBM_CUDA(c, launch_step(c, z_begin, z_end, update_macro != 0, c->stream));
+    return LBM_OK;
+}
+
+int lbm_advance(lbm_ctx *c)
+{
+    if (!c) return LBM_ERR_INVALID;
+    if (!c->initialised) return fail(c, LBM_ERR_STATE, "lbm_advance before lbm_init");
+    c->cur ^= 1;
+    c->iteration += 1;
+    return LBM_OK;
+}
+
+int lbm_z_range(const lbm_ctx *c, int32_t *z_begin, int32_t *z_end)
+{
+    if (!c) return LBM_ERR_INVALID;
+    if (z_begin) *z_begin = c->z_begin;
+    if (z_end) *z_end = c->z_end;
     return LBM_OK;
 }
 

@@ -58,7 +58,19 @@ struct StepArgs {
     Layout lay;
     Consts<T> c;
     T stale[2][Q];              // [0]: w_q (rest equilibrium); [1]: f_eq_q(1, (U,0,0)); see header
+    // Byte offsets precomputed by the host (uniform; they live in the constant bank):
+    //   goff[q]  from the address of (x, y, z, 0) to the address of (x, y - ey, z - ez, q)   [LM_ROWS / LM_SOA]
+    //   soff[q]  from the address of (x, y, z, 0) to the address of (x, y, z, q)
+    long long goff[Q];
+    long long soff[Q];
 };
+
+// How neighbour addresses are formed (chosen by the host from stride and DIM):
+//   LM_GENERIC  any stride: full CSoA index computation per access;
+//   LM_ROWS     stride <= DIM: every x-row starts a CSoA block, so a shift in y or z is a constant
+//               address offset and only the x position inside the row needs the block arithmetic;
+//   LM_SOA      stride >= number of stored cells: one block, every neighbour is a constant offset.
+enum : int { LM_GENERIC = 0, LM_ROWS = 1, LM_SOA = 2 };
 
 template <typename T>
 struct InitArgs {
@@ -209,7 +221,7 @@ __device__ __forceinline__ void bounce_back(T (&f)[Q])
 //   x0 .. x0+VEC-1 = (blockIdx.x*bx + tx)*VEC .. ,  y = blockIdx.y*by + ty,  z = z_begin + blockIdx.z*bz + tz.
 // Requirements (checked by the host): bx a power of two, bx*VEC divides DIM, by divides DIM,
 // VEC divides stride (so every vector is aligned and inside one CSoA run).
-template <typename T, int VEC, bool FAST, bool MACRO, bool PEER>
+template <typename T, int VEC, bool FAST, bool MACRO, bool PEER, int LM>
 __global__ void __launch_bounds__(256) step_pull_kernel(const StepArgs<T> a)
 {
     using V = Pack<T, VEC>;
@@ -228,13 +240,42 @@ __global__ void __launch_bounds__(256) step_pull_kernel(const StepArgs<T> a)
     const long long id0 = x0 + (long long)y * dim + (long long)(z - a.zs0) * plane;
     const long long qp = a.lay.qpitch();
 
+    // ---- addresses: one per-thread base, per-direction offsets are uniform ----
+    // b0 = element index of (x0, y, z, q = 0); bm / bp = of (x0 - 1, ..) and (x0 + VEC, ..), clamped
+    // into the row (the clamped values are only ever consumed by WALL cells).
+    long long b0, bm, bp;
+    if constexpr (LM == LM_ROWS) {
+        const long long rowbase = ((long long)y * dim + (long long)(z - a.zs0) * plane) * Q;
+        const int xm = x0 > 0 ? x0 - 1 : 0;
+        const int xp = x0 + VEC < dim ? x0 + VEC : dim - 1;
+        const int sm = (int)a.lay.smod;
+        b0 = rowbase + ((((x0 >> a.lay.sdiv) * Q) << a.lay.sdiv) + (x0 & sm));
+        bm = rowbase + ((((xm >> a.lay.sdiv) * Q) << a.lay.sdiv) + (xm & sm));
+        bp = rowbase + ((((xp >> a.lay.sdiv) * Q) << a.lay.sdiv) + (xp & sm));
+    } else if constexpr (LM == LM_SOA) {
+        b0 = id0;
+        bm = id0 - 1;  // live rows have y >= 1, so id0 >= DIM
+        bp = id0 + VEC;
+    } else {
+        b0 = a.lay.base(id0);
+        bm = bp = 0;
+    }
+    const char *const s0 = reinterpret_cast<const char *>(a.src + b0);
+    const char *const sm1 = reinterpret_cast<const char *>(a.src + bm);
+    const char *const sp1 = reinterpret_cast<const char *>(a.src + bp);
+
     // ---- gather: f[q][j] = G(x0 + j - ex, y - ey, z - ez, q) ----
     T f[Q][VEC];
     if constexpr (VEC == 1) {
         static_for<Q>([&](auto qc) {
             constexpr int q = decltype(qc)::value;
-            const long long sid = id0 - ex(q) - (long long)ey(q) * dim - (long long)ez(q) * plane;
-            f[q][0] = a.src[a.lay.base(sid) + q * qp];
+            if constexpr (LM == LM_GENERIC) {
+                const long long sid = id0 - ex(q) - (long long)ey(q) * dim - (long long)ez(q) * plane;
+                f[q][0] = a.src[a.lay.base(sid) + q * qp];
+            } else {
+                const char *p = ex(q) == 0 ? s0 : (ex(q) == 1 ? sm1 : sp1);
+                f[q][0] = *reinterpret_cast<const T *>(p + a.goff[q]);
+            }
         });
     } else {
         // lanes of one row segment are consecutive lanes of the warp
@@ -243,21 +284,31 @@ __global__ void __launch_bounds__(256) step_pull_kernel(const StepArgs<T> a)
         const bool seg_last = (tx & (seg - 1)) == seg - 1;
         static_for<Q>([&](auto qc) {
             constexpr int q = decltype(qc)::value;
-            const long long sid = id0 - (long long)ey(q) * dim - (long long)ez(q) * plane;
-            const T *p = a.src + q * qp;
-            const V v = *reinterpret_cast<const V *>(p + a.lay.base(sid));
+            V v;
+            const T *pe_m, *pe_p;  // where the element left of / right of the vector lives
+            if constexpr (LM == LM_GENERIC) {
+                const long long sid = id0 - (long long)ey(q) * dim - (long long)ez(q) * plane;
+                const T *p = a.src + q * qp;
+                v = *reinterpret_cast<const V *>(p + a.lay.base(sid));
+                pe_m = p + (ex(q) == 1 ? a.lay.base(sid - 1) : 0);
+                pe_p = p + (ex(q) == -1 ? a.lay.base(sid + VEC) : 0);
+            } else {
+                v = *reinterpret_cast<const V *>(s0 + a.goff[q]);
+                pe_m = reinterpret_cast<const T *>(sm1 + a.goff[q]);
+                pe_p = reinterpret_cast<const T *>(sp1 + a.goff[q]);
+            }
             if constexpr (ex(q) == 0) {
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) f[q][j] = v.v[j];
             } else if constexpr (ex(q) == 1) {
                 T e = __shfl_up_sync(mask, v.v[VEC - 1], 1);
-                if (seg_first) e = (x0 > 0) ? p[a.lay.base(sid - 1)] : T(0);
+                if (seg_first) e = (x0 > 0) ? *pe_m : T(0);
                 f[q][0] = e;
 #pragma unroll
                 for (int j = 1; j < VEC; ++j) f[q][j] = v.v[j - 1];
             } else {
                 T e = __shfl_down_sync(mask, v.v[0], 1);
-                if (seg_last) e = (x0 + VEC < dim) ? p[a.lay.base(sid + VEC)] : T(0);
+                if (seg_last) e = (x0 + VEC < dim) ? *pe_p : T(0);
                 f[q][VEC - 1] = e;
 #pragma unroll
                 for (int j = 0; j < VEC - 1; ++j) f[q][j] = v.v[j + 1];
@@ -315,13 +366,13 @@ __global__ void __launch_bounds__(256) step_pull_kernel(const StepArgs<T> a)
     }
 
     // ---- store G_k ----
-    const long long b0 = a.lay.base(id0);
+    char *const d0 = reinterpret_cast<char *>(a.dst + b0);
     static_for<Q>([&](auto qc) {
         constexpr int q = decltype(qc)::value;
         V v;
 #pragma unroll
         for (int j = 0; j < VEC; ++j) v.v[j] = f[q][j];
-        *reinterpret_cast<V *>(a.dst + b0 + q * qp) = v;
+        *reinterpret_cast<V *>(d0 + a.soff[q]) = v;
         if constexpr (PEER) {
             // fused halo exchange: the five populations that cross the slab face also go straight
             // into the neighbour's halo plane (NVLink stores when the neighbour is a peer device)
