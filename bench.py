@@ -229,6 +229,7 @@ def run_b200(a):
     import torch
     import torch.distributed as dist
     from lbmcl_b200.capi import Simulation
+    from lbmcl_b200.slabs import exchange_halos, slab_range
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -244,10 +245,8 @@ def run_b200(a):
         dist.init_process_group("nccl", device_id=dev)
 
     dim = a.dim or (256 if world == 1 else 1024)
-    if dim % world != 0:
-        raise SystemExit(f"dim {dim} not divisible by {world} ranks")
-    nz = dim // world
-    z0, z1 = rank * nz, (rank + 1) * nz
+    z0, z1 = slab_range(dim, world, rank)
+    nz = z1 - z0
     block = tuple(int(v) for v in a.block.split(",")) if a.block else (256, 1, 1)
     esize = 4 if a.precision == "f32" else 8
     npdtype = np.float32 if a.precision == "f32" else np.float64
@@ -294,12 +293,7 @@ def run_b200(a):
             sim.set_stream(bstream.cuda_stream)
             sim.halo_pack()
             with torch.cuda.stream(bstream):
-                ops = []
-                if has_hi:
-                    ops += [dist.P2POp(dist.isend, send[1], rank + 1), dist.P2POp(dist.irecv, recv[1], rank + 1)]
-                if has_lo:
-                    ops += [dist.P2POp(dist.isend, send[0], rank - 1), dist.P2POp(dist.irecv, recv[0], rank - 1)]
-                for r in dist.batch_isend_irecv(ops):
+                for r in exchange_halos(send, recv, world, rank):
                     r.wait()
             sim.halo_unpack()
             sim.set_stream(main.cuda_stream)

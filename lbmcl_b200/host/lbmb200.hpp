@@ -1,0 +1,467 @@
+// LBMCL<T>: the simulation driver of the LBMCL host program, re-implemented over the C ABI of
+// liblbm_b200.so (include/lbm_b200.h) instead of the OpenCL C++ bindings.
+//
+// Public surface = what reference main.cpp drives (reference lbmcl.hpp): the 14-argument constructor
+// (:338-388), setupSimulation (:392), printConfiguration (:623), performSimulation (:485-521),
+// waitCompletion (:525), performSimulationAndWait (:538), totalTimeMS (:548), kernelsTimeMS (:562),
+// kernelsTimingsMS (:580), MLUPS (:604), kernelsMLUPS (:617), statistics (:648).  File formats are the
+// reference's: lbmcl.<it>.vti (:261-334), map.dump (:159-203), f_<it>.dump (:206-258).
+//
+// Differences, all forced by the change of device runtime:
+//   * no platform; the device id is a CUDA ordinal and a negative id means device 0 instead of an
+//     interactive prompt (reference CLUtil.hpp:126-138);
+//   * the work-group size is a hint (lbm_block_shape reports the CUDA block actually used);
+//   * optional z-slab decomposition over several GPUs (`gpus` > 1);
+//   * device errors are reported as "file:line what(code) - cudaErrorName" by the library and end the
+//     program with a non-zero status here (reference CLUtil.hpp:101-117 does the same with CL names);
+//   * the ASCII VTI body is formatted by several host threads (identical bytes, less wall time).
+#pragma once
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iomanip>
+#include <iostream>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <type_traits>
+#include <utility>
+#include <vector>
+
+#include "../../include/lbm_b200.h"
+
+#define LBM_INITIALIZE_KERNEL_NAME "initialize"
+#define LBM_COMPUTE_KERNEL_NAME "compute"
+
+template <typename T>
+class LBMCL {
+    static_assert(std::is_same<T, float>::value || std::is_same<T, double>::value,
+                  "Only float or double data type is valid.");
+
+    size_t dim;
+    T viscosity;
+    T velocity;
+    size_t iterations;
+    size_t every;
+    std::string vtk_path;
+    size_t lws[3];
+    size_t stride;
+    bool optimize;
+    std::string dump_path;
+    bool dump_map;
+    bool dump_f;
+    bool dump_data;
+    int gpus;
+
+    lbm_ctx *ctx = nullptr;
+    lbm_group *group = nullptr;
+    std::string device_name = "?";
+    int64_t device_bytes = 0;
+
+    std::vector<T> rho_values, u_values, f_values;
+    std::vector<int32_t> map_values;
+
+    static constexpr size_t Q = 19, D = 3;
+
+    size_t cells() const { return dim * dim * dim; }
+    size_t wet_dim() const { return (dim - 2) * (dim - 2) * (dim - 2); }
+    static size_t digits(size_t v) { return v > 0 ? (size_t)std::log10((double)v) + 1 : 1; }  // lbmcl.hpp:13
+    static bool is_pow2(size_t x) { return x && !(x & (x - 1)); }
+    static size_t floor_pow2(size_t x)
+    {
+        size_t p = 1;
+        while (p * 2 <= x && p * 2 != 0) p *= 2;
+        return x ? p : 0;
+    }
+    static size_t log2i(size_t x)
+    {
+        size_t n = 0;
+        for (; x > 1; x >>= 1) ++n;
+        return n;
+    }
+
+    [[noreturn]] void die(int code, const char *what) const
+    {
+        const char *msg = group ? lbm_group_last_error(group) : lbm_last_error(ctx);
+        std::cerr << what << " failed (" << code << "): " << (msg ? msg : "") << std::endl;
+        std::exit(code == 0 ? 1 : (code < 0 ? -code : code));
+    }
+    void check(int rc, const char *what) const
+    {
+        if (rc != LBM_OK) die(rc, what);
+    }
+
+    // what lbmcl.hpp:131-156 hands to the OpenCL compiler; kept as the description of the
+    // specialisation (the same values parameterise the CUDA kernels)
+    std::string kernelOptionsStr() const
+    {
+        std::stringstream o;
+        o << "-DDIM=" << dim << " -DLWS=" << lws[0] << " -DSTRIDE_DIV=" << log2i(stride) << " -DSTRIDE_MOD="
+          << (stride - 1) << " -DVISCOSITY=" << viscosity << " -DVELOCITY=" << velocity << " ";
+        o << (std::is_same<T, float>::value ? "-DFP_SINGLE " : "-DFP_DOUBLE ");
+        if (optimize) o << "-use_fast_math ";
+        o << "[sm_100a";
+        if (gpus > 1) o << ", " << gpus << " z-slabs";
+        o << "]";
+        return o.str();
+    }
+
+    std::string numbered(const std::string &dir, const char *stem, size_t it, const char *ext) const
+    {
+        std::stringstream s;
+        s << dir << "/" << stem << std::setw((int)digits(iterations)) << std::setfill('0') << it << ext;
+        return s.str();
+    }
+
+    void readMacros()
+    {
+        if (group) check(lbm_group_read_macros(group, rho_values.data(), u_values.data()), "read_rho/read_u");
+        else check(lbm_read_macros(ctx, rho_values.data(), u_values.data()), "read_rho/read_u");
+    }
+
+    // map.dump, lbmcl.hpp:159-203.  A missing directory is a silent no-op there (no check on the
+    // ofstream) and here.
+    void storeMap()
+    {
+        check(lbm_read_map(group ? lbm_group_ctx(group, 0) : ctx, map_values.data()), "read_map");
+        FILE *fp = std::fopen((dump_path + "/map.dump").c_str(), "w");
+        if (!fp) return;
+        std::fputs("# FLUID       1\n# MOVING      2\n# BOUNDARY    3\n# WALL        4\n# CORNER      5\n\n", fp);
+        std::string line;
+        for (size_t z = 0; z < dim; ++z) {
+            for (size_t y = 0; y < dim; ++y) {
+                line.clear();
+                for (size_t x = 0; x < dim; ++x) {
+                    const int t = map_values[x + y * dim + z * dim * dim];
+                    // the reference assigns the categories in sequence, later ones win (:188-193):
+                    // lid cells carry the FRONT bit and therefore print 3, not 2
+                    int v = 0;
+                    if (t == 0x1) v = 1;
+                    if (t & 0x2) v = 2;
+                    if (t & 0x3f0) v = 3;
+                    if (t == 0x8) v = 4;
+                    if (t == 0x4) v = 5;
+                    line += (char)('0' + v);
+                    line += ' ';
+                }
+                line += '\n';
+                std::fputs(line.c_str(), fp);
+            }
+            std::fputc('\n', fp);
+        }
+        std::fputc('\n', fp);
+        std::fclose(fp);
+    }
+
+    // f_<it>.dump, lbmcl.hpp:206-258: the populations iteration `it` reads, CSoA order.
+    void storeF(size_t iteration)
+    {
+        check(lbm_read_f(ctx, f_values.data()), "read_f");
+        FILE *fp = std::fopen(numbered(dump_path, "f_", iteration, ".dump").c_str(), "w");
+        if (!fp) return;
+        const int dd = (int)digits(dim);
+        const size_t coord_spaces = (size_t)dd * 3 + 5;
+        std::string head(coord_spaces, ' ');
+        char buf[128];
+        for (size_t q = 0; q < Q; ++q) {
+            std::snprintf(buf, sizeof buf, "%8zu ", q);
+            head += buf;
+        }
+        head += '\n';
+        std::string line;
+        for (size_t z = 0; z < dim; ++z) {
+            for (size_t y = 0; y < dim; ++y) {
+                std::fputs(head.c_str(), fp);
+                for (size_t x = 0; x < dim; ++x) {
+                    const size_t id = x + y * dim + z * dim * dim;
+                    std::snprintf(buf, sizeof buf, "%*s%u,%u,%u) ", dd, "(", (unsigned)x, (unsigned)y, (unsigned)z);
+                    line = buf;
+                    for (size_t q = 0; q < Q; ++q) {
+                        const T v = f_values[((id / stride) * Q + q) * stride + (id & (stride - 1))];
+                        std::snprintf(buf, sizeof buf, "%8.6f ", (double)v);
+                        line += buf;
+                    }
+                    line += '\n';
+                    std::fputs(line.c_str(), fp);
+                }
+                std::fputc('\n', fp);
+            }
+            std::fputc('\n', fp);
+        }
+        std::fputc('\n', fp);
+        std::fclose(fp);
+    }
+
+    // "%.16e " exactly as operator<< with std::scientific and precision 16 prints it
+    static void put(std::string &out, T v)
+    {
+        char buf[40];
+        const int n = std::snprintf(buf, sizeof buf, "%.16e ", (double)v);
+        out.append(buf, (size_t)n);
+    }
+
+    // lbmcl.<it>.vti, lbmcl.hpp:261-334: rho then 3-component v over the wet cube, x fastest.
+    void storeData(size_t iteration)
+    {
+        readMacros();
+        FILE *fp = std::fopen(numbered(vtk_path, "lbmcl.", iteration, ".vti").c_str(), "w");
+        if (!fp) return;
+        const size_t from = 1, to = dim - 1, extent = to - from - 1, n = cells();
+        const char *type = std::is_same<T, float>::value ? "Float32" : "Float64";
+        std::fprintf(fp,
+                     "<?xml version=\"1.0\"?>\n"
+                     "<VTKFile type=\"ImageData\" version=\"0.1\" byte_order=\"LittleEndian\" header_type=\"UInt64\">\n"
+                     "  <ImageData WholeExtent=\"0 %zu 0 %zu 0 %zu\" Origin=\"0 0 0\" Spacing=\"1 1 1\">\n"
+                     "    <Piece Extent=\"0 %zu 0 %zu 0 %zu\">\n"
+                     "      <PointData Scalars=\"rho\">\n"
+                     "        <DataArray type=\"%s\" Name=\"rho\" NumberOfComponents=\"1\" format=\"ascii\">\n",
+                     extent, extent, extent, extent, extent, extent, type);
+
+        // format z-planes in parallel, write them in order
+        const size_t planes = to - from;
+        unsigned nthreads = std::thread::hardware_concurrency();
+        if (nthreads == 0) nthreads = 1;
+        if (nthreads > 32) nthreads = 32;
+        if (nthreads > planes) nthreads = (unsigned)planes;
+        if (nthreads == 0) nthreads = 1;
+        for (int pass = 0; pass < 2; ++pass) {
+            std::vector<std::string> chunk(planes);
+            auto work = [&](unsigned tid) {
+                for (size_t k = tid; k < planes; k += nthreads) {
+                    const size_t z = from + k;
+                    std::string &out = chunk[k];
+                    out.reserve((to - from) * (to - from) * (pass == 0 ? 24 : 72) + 64);
+                    for (size_t y = from; y < to; ++y) {
+                        for (size_t x = from; x < to; ++x) {
+                            const size_t id = x + y * dim + z * dim * dim;
+                            if (pass == 0) {
+                                put(out, rho_values[id]);
+                            } else {
+                                put(out, u_values[0 * n + id]);
+                                put(out, u_values[1 * n + id]);
+                                put(out, u_values[2 * n + id]);
+                            }
+                        }
+                        out += '\n';
+                    }
+                }
+            };
+            std::vector<std::thread> pool;
+            for (unsigned t = 1; t < nthreads; ++t) pool.emplace_back(work, t);
+            work(0);
+            for (auto &t : pool) t.join();
+            for (const std::string &c : chunk) std::fwrite(c.data(), 1, c.size(), fp);
+            if (pass == 0)
+                std::fprintf(fp,
+                             "        </DataArray>\n"
+                             "        <DataArray type=\"%s\" Name=\"v\" NumberOfComponents=\"3\" format=\"ascii\">\n",
+                             type);
+        }
+        std::fputs("        </DataArray>\n      </PointData>\n    </Piece>\n  </ImageData>\n</VTKFile>\n", fp);
+        std::fclose(fp);
+    }
+
+public:
+    LBMCL(size_t dim, T viscosity, T velocity, size_t iterations, size_t every, std::string vtk_path = "",
+          size_t lwx = 1, size_t lwy = 1, size_t lwz = 1, size_t stride = 32, bool optimize = true,
+          std::string dump_path = "", bool dump_map = false, bool dump_f = false, int gpus = 1)
+        : dim(dim), viscosity(viscosity), velocity(velocity), iterations(iterations), every(every),
+          vtk_path(std::move(vtk_path)), stride(stride), optimize(optimize), dump_path(std::move(dump_path)),
+          dump_map(dump_map), dump_f(dump_f), dump_data(every != 0), gpus(gpus < 1 ? 1 : gpus)
+    {
+        if (!is_pow2(this->dim)) {  // lbmcl.hpp:364-367
+            this->dim = floor_pow2(this->dim);
+            std::cout << "dim is rounded to the previous power of 2: " << this->dim << std::endl;
+        }
+        lws[0] = lwx ? lwx : 1;
+        lws[1] = lwy ? lwy : 1;
+        lws[2] = lwz ? lwz : 1;
+        if (lws[0] * lws[1] * lws[2] > this->dim * this->dim * this->dim) {  // lbmcl.hpp:375-378
+            std::cerr << "Please enter a good work_group_size to run the simulation" << std::endl;
+            std::exit(-1);
+        }
+        if (!is_pow2(this->stride)) {  // lbmcl.hpp:384-387
+            this->stride = floor_pow2(this->stride);
+            std::cout << "stride is rounded to the previous power of 2: " << this->stride << std::endl;
+        }
+    }
+
+    LBMCL(const LBMCL &) = delete;
+    LBMCL &operator=(const LBMCL &) = delete;
+
+    ~LBMCL()
+    {
+        if (group) lbm_group_destroy(group);
+        if (ctx) lbm_destroy(ctx);
+    }
+
+    // lbmcl.hpp:392-482.  platformID is accepted for compatibility and ignored.
+    void setupSimulation(int /*platformID*/, int deviceID)
+    {
+        lbm_params p;
+        lbm_default_params(&p);
+        p.dim = (int32_t)dim;
+        p.precision = std::is_same<T, float>::value ? LBM_F32 : LBM_F64;
+        p.fast_math = optimize ? 1 : 0;
+        p.viscosity = (double)viscosity;
+        p.velocity = (double)velocity;
+        p.stride = (int64_t)stride;
+        p.block_x = (int32_t)lws[0];
+        p.block_y = (int32_t)lws[1];
+        p.block_z = (int32_t)lws[2];
+        p.device = deviceID < 0 ? 0 : deviceID;
+        p.variant = LBM_VARIANT_AUTO;
+        if (const char *v = std::getenv("LBM_VARIANT")) p.variant = std::atoi(v);
+        char name[256] = "?";
+        if (gpus > 1) {
+            std::vector<int32_t> devs;
+            for (int i = 0; i < gpus; ++i) devs.push_back(p.device + i);
+            const int rc = lbm_group_create(&p, devs.data(), gpus, &group);
+            if (rc != LBM_OK) {
+                std::cerr << "lbm_group_create failed (" << rc << "): " << lbm_group_last_error(nullptr) << std::endl;
+                std::exit(-rc);
+            }
+            lbm_device_name(lbm_group_ctx(group, 0), name, sizeof name);
+            for (int i = 0; i < gpus; ++i) device_bytes += lbm_device_bytes(lbm_group_ctx(group, i));
+        } else {
+            const int rc = lbm_create(&p, &ctx);
+            if (rc != LBM_OK) {
+                std::cerr << "lbm_create failed (" << rc << "): " << lbm_last_error(nullptr) << std::endl;
+                std::exit(-rc);
+            }
+            lbm_device_name(ctx, name, sizeof name);
+            device_bytes = lbm_device_bytes(ctx);
+        }
+        device_name = name;
+        if (dump_f && gpus > 1) {
+            std::cerr << "-f (dump_f) needs the whole cube on one device; run without --gpus" << std::endl;
+            std::exit(1);
+        }
+        if (dump_map) map_values.resize(cells());
+        if (dump_f) f_values.resize(cells() * Q);
+        if (dump_data) {
+            rho_values.resize(cells());
+            u_values.resize(cells() * D);
+        }
+    }
+
+    // lbmcl.hpp:485-521.  Kernel launches are asynchronous; the store* calls block like the reference's
+    // blocking enqueueReadBuffer calls do.
+    void performSimulation()
+    {
+        if (group) check(lbm_group_init(group), LBM_INITIALIZE_KERNEL_NAME);
+        else check(lbm_init(ctx), LBM_INITIALIZE_KERNEL_NAME);
+        if (dump_map) storeMap();
+        if (dump_data) storeData(0);
+        if (dump_f) storeF(0);
+
+        size_t it = 0;
+        while (it < iterations) {
+            if (dump_f) {
+                // f_<it+1>.dump holds what iteration it+1 reads (lbmcl.hpp:517-519): fetch it before the launch
+                storeF(it + 1);
+                check(lbm_step(ctx, (dump_data && ((it + 1) % every == 0)) ? 1 : 0), LBM_COMPUTE_KERNEL_NAME);
+                ++it;
+            } else {
+                // run up to the next iteration that stores data in one asynchronous batch
+                size_t chunk = iterations - it;
+                if (dump_data) {
+                    const size_t to_next = every - (it % every);
+                    if (to_next < chunk) chunk = to_next;
+                }
+                const int ev = dump_data ? (int)every : 0;
+                if (group) check(lbm_group_run(group, (int)chunk, ev), LBM_COMPUTE_KERNEL_NAME);
+                else check(lbm_run(ctx, (int)chunk, ev), LBM_COMPUTE_KERNEL_NAME);
+                it += chunk;
+            }
+            if (dump_data && it % every == 0) storeData(it);
+        }
+    }
+
+    void waitCompletion()  // lbmcl.hpp:525-532
+    {
+        if (group) check(lbm_group_sync(group), "finish");
+        else check(lbm_sync(ctx), "finish");
+    }
+
+    void performSimulationAndWait()
+    {
+        performSimulation();
+        waitCompletion();
+    }
+
+    // first event start -> last event end, read-backs and file writing in between included
+    // (lbmcl.hpp:548-556)
+    double totalTimeMS()
+    {
+        double total = 0.0;
+        if (group) check(lbm_group_time_ms(group, &total, nullptr), "time");
+        else check(lbm_time_ms(ctx, &total, nullptr), "time");
+        return total;
+    }
+
+    // sum over the compute launches only (lbmcl.hpp:562-574)
+    double kernelsTimeMS()
+    {
+        double k = 0.0;
+        if (group) check(lbm_group_time_ms(group, nullptr, &k), "time");
+        else check(lbm_time_ms(ctx, nullptr, &k), "time");
+        return k;
+    }
+
+    // lbmcl.hpp:580-593.  Launches are timed per asynchronous batch here, so the list has the two
+    // aggregate entries rather than one entry per launch.
+    std::vector<std::pair<std::string, double>> kernelsTimingsMS()
+    {
+        std::vector<std::pair<std::string, double>> t;
+        const double k = kernelsTimeMS();
+        t.emplace_back(LBM_INITIALIZE_KERNEL_NAME, totalTimeMS() - k);
+        t.emplace_back(LBM_COMPUTE_KERNEL_NAME, k);
+        return t;
+    }
+
+    double MLUPS() { return (wet_dim() * iterations) / (totalTimeMS() * 1000); }           // lbmcl.hpp:604-607
+    double kernelsMLUPS() { return (wet_dim() * iterations) / (kernelsTimeMS() * 1000); }  // lbmcl.hpp:617-620
+
+    void printConfiguration()  // lbmcl.hpp:623-645
+    {
+        const char *prec = std::is_same<T, float>::value ? "single" : "double";
+        int32_t blk[3] = {0, 0, 0}, vec = 0;
+        lbm_block_shape(group ? lbm_group_ctx(group, 0) : ctx, blk, &vec);
+        std::cout << std::boolalpha
+                  << "kernel options   = " << kernelOptionsStr() << "\n"
+                  << "device           = " << device_name << "\n"
+                  << "dim              = " << dim << "\n"
+                  << "viscosity        = " << viscosity << "\n"
+                  << "velocity         = " << velocity << "\n"
+                  << "Device Mem. (B)  = " << device_bytes << "\n"
+                  << "Device Mem. (KB) = " << device_bytes / (1 << 10) << "\n"
+                  << "Device Mem. (MB) = " << device_bytes / (1 << 20) << "\n"
+                  << "iterations       = " << iterations << "\n"
+                  << "work_group_size  = (" << lws[0] << ", " << lws[1] << ", " << lws[2] << ")\n"
+                  << "stride           = " << stride << "\n"
+                  << "precision        = " << prec << "\n"
+                  << "optimize         = " << optimize << "\n"
+                  << "every            = " << every << "\n"
+                  << "VTK PATH         = " << vtk_path << "\n"
+                  << "DUMP F           = " << dump_f << "\n"
+                  << "DUMP MAP         = " << dump_map << "\n"
+                  << "CUDA block       = (" << blk[0] << ", " << blk[1] << ", " << blk[2] << ") x " << vec
+                  << " cell(s)/thread, " << gpus << " GPU(s)\n";
+    }
+
+    // lbmcl.hpp:648-669; the line benchmark.sh:111-176 aggregates
+    std::string statistics(char separator)
+    {
+        const char *prec = std::is_same<T, float>::value ? "single" : "double";
+        std::stringstream s;
+        s << device_name << separator << prec << separator << dim << separator << iterations << separator << every
+          << separator << std::setw(3) << std::setfill('0') << lws[0] << "," << std::setw(3) << std::setfill('0')
+          << lws[1] << "," << std::setw(3) << std::setfill('0') << lws[2] << separator << stride << separator
+          << optimize << separator << totalTimeMS() << separator << kernelsTimeMS() << separator << MLUPS()
+          << separator << kernelsMLUPS() << "\n";
+        return s.str();
+    }
+};

@@ -1,0 +1,57 @@
+"""z-slab decomposition: host-side plan for the one-process-per-GPU mode (new functionality; the
+reference is single-device).
+
+The cube is cut into `world` slabs of DIM/world planes.  Per iteration each rank sends, per interior
+face, the 5 populations that cross it (packed densely by lbm_halo_pack: [5][DIM][DIM]) and receives
+the neighbour's; nothing else is communicated and there is no collective on the data path.
+Transport is torch.distributed point-to-point (NCCL over NVLink on the GPUs; gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+# populations with e_z = +1 / -1 (reference kernels.cl:151-205)
+UP_Q = (6, 15, 16, 17, 18)
+DOWN_Q = (5, 11, 12, 13, 14)
+FACE_LOW, FACE_HIGH = 0, 1
+
+
+def slab_range(dim: int, world: int, rank: int):
+    """Owned global planes [z0, z1) of `rank`."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError(f"bad rank {rank} of {world}")
+    if dim % world != 0:
+        raise ValueError(f"dim {dim} is not divisible into {world} z-slabs")
+    nz = dim // world
+    return rank * nz, (rank + 1) * nz
+
+
+def neighbours(world: int, rank: int):
+    """(rank below or None, rank above or None)"""
+    return (rank - 1 if rank > 0 else None, rank + 1 if rank < world - 1 else None)
+
+
+def halo_elems(dim: int) -> int:
+    return 5 * dim * dim
+
+
+def halo_bytes_per_step(dim: int, world: int, rank: int, itemsize: int) -> int:
+    lo, hi = neighbours(world, rank)
+    return sum(1 for n in (lo, hi) if n is not None) * halo_elems(dim) * itemsize
+
+
+def exchange_halos(send, recv, world: int, rank: int, group=None):
+    """Post this rank's sends/receives as one batch (ncclGroupStart/End under NCCL) and return the
+    request handles.  `send` / `recv` are [low, high] lists of 1-D tensors (None on a cube face).
+
+    My HIGH face talks to the LOW face of rank+1 and vice versa; posting everything in one batch makes
+    the order of the operations irrelevant, so no rank can deadlock on its neighbour."""
+    import torch.distributed as dist
+
+    lo, hi = neighbours(world, rank)
+    ops = []
+    if hi is not None:
+        ops.append(dist.P2POp(dist.isend, send[FACE_HIGH], hi, group))
+        ops.append(dist.P2POp(dist.irecv, recv[FACE_HIGH], hi, group))
+    if lo is not None:
+        ops.append(dist.P2POp(dist.isend, send[FACE_LOW], lo, group))
+        ops.append(dist.P2POp(dist.irecv, recv[FACE_LOW], lo, group))
+    return dist.batch_isend_irecv(ops) if ops else []

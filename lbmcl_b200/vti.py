@@ -117,7 +117,7 @@ def write_vti_ascii(path: str, rho: np.ndarray, v: np.ndarray, dim: int) -> None
     """Write ``rho[N]`` / ``v[3][N]`` (N = dim^3, x fastest) the way reference lbmcl.hpp:261-334 does.
 
     Only the wet cube x,y,z in [1, dim-2] is written; values are printed in scientific notation with
-    16 digits.  Used by tests to produce files from oracle output; the product's writer is the C++
+    16 digits.  Used by the tests to produce files from CPU-side arrays; the product's writer is the C++
     host (lbmcl_b200/host/lbmb200.hpp).
     """
     n = dim ** 3

@@ -1,0 +1,86 @@
+"""The drop-in boundary on a box without a GPU: the C-ABI library loads, exports every symbol that
+include/lbm_b200.h declares, validates its arguments, and refuses to run without a CUDA device (no
+CPU fallback).  No compute call is made here."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+HEADER = os.path.join(ROOT, "include", "lbm_b200.h")
+
+
+def _declared_functions():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(lbm_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from lbmcl_b200 import capi
+    lib = capi.load()
+    names = _declared_functions()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), f"liblbm_b200.so does not export {n}"
+    assert sorted(capi.EXPORTS) == names, "capi.EXPORTS and include/lbm_b200.h disagree"
+
+
+def test_default_params_are_the_reference_defaults():
+    from lbmcl_b200 import capi
+    p = capi.LbmParams()
+    capi.load().lbm_default_params(ctypes.byref(p))
+    # lbm_options.hpp:32-50
+    assert (p.dim, p.viscosity, p.velocity, p.stride) == (8, 0.0089, 0.05, 32)
+    assert (p.block_x, p.block_y, p.block_z) == (8, 8, 8)
+    assert p.precision == capi.F32 and p.fast_math == 0 and p.abi_version == capi.ABI_VERSION
+    assert ctypes.sizeof(capi.LbmParams) == 104
+
+
+@pytest.mark.parametrize("kw,fragment", [
+    (dict(dim=12), "power of two"),
+    (dict(dim=2), "power of two"),
+    (dict(dim=8, stride=24), "stride"),
+    (dict(dim=8, stride=1024), "stride"),          # > dim^3: the reference would overrun its buffers
+    (dict(dim=8, viscosity=-1.0), "viscosity"),
+    (dict(dim=8, z_range=(4, 2)), "z range"),
+    (dict(dim=8, variant=3), "variant"),
+])
+def test_invalid_configurations_are_rejected(kw, fragment):
+    from lbmcl_b200.capi import LbmError, Simulation
+    with pytest.raises(LbmError) as e:
+        Simulation(**kw)
+    assert e.value.code == -1 and fragment in str(e.value)
+
+
+def test_abi_version_is_checked():
+    from lbmcl_b200 import capi
+    p = capi.make_params(dim=8)
+    p.abi_version = 99
+    h = ctypes.c_void_p()
+    assert capi.load().lbm_create(ctypes.byref(p), ctypes.byref(h)) == -1
+    assert b"abi_version" in capi.load().lbm_last_error(None)
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path must fail loudly, never compute on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from lbmcl_b200.capi import LbmError, Simulation
+    with pytest.raises(LbmError) as e:
+        Simulation(dim=8)
+    assert e.value.code == -3 and "no CPU path" in str(e.value)
+
+
+def test_product_path_does_not_touch_the_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may use oracle/."""
+    pkg = os.path.join(ROOT, "lbmcl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".cpp", ".inl", ".h")) or f == "Makefile":
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "import oracle" not in text and "from oracle import" not in text, f
+                assert "liblbm_oracle" not in text and "oracle/_ref" not in text, f

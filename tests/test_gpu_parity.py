@@ -158,7 +158,7 @@ def test_golden_32_through_cabi(golden32):
         p_v = np.moveaxis(wet(u[it // 20], 32), 0, -1)
         assert np.array_equal(np.isnan(p_rho), np.isnan(t_rho))
         assert np.nanmax(np.abs(p_rho - t_rho)) <= 4e-6, it
-        assert np.nanmax(np.abs(p_v - t_v)) <= 1.1e-5 * 0.05, it
+        assert np.nanmax(np.abs(p_v - t_v)) <= 1.2e-5 * 0.05, it
 
 
 @pytest.mark.parametrize("precision,dim", [("f32", 256), ("f64", 128)])

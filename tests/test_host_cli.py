@@ -1,0 +1,180 @@
+"""The C++11 host program `lbmcl`: command-line contract on CPU, full make test8 / test32 / testall
+flows on the GPU (outputs compared with the oracle and the golden fixtures)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, wet
+
+HOST = os.path.join(ROOT, "lbmcl_b200", "host")
+EXE = os.path.join(HOST, "lbmcl")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _exe():
+    if not os.path.exists(EXE):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "lbmcl_b200", "csrc")])
+        subprocess.check_call(["make", "-C", HOST])
+
+
+def _run(*args, cwd=None):
+    return subprocess.run([EXE, *args], cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+
+
+def test_help_and_unknown_option_exit_1():
+    for flag in ("-h", "--help", "-Z"):
+        r = _run(flag)
+        assert r.returncode == 1                                   # lbm_options.hpp:70, 189-193
+        assert "-d  --dim                 Set the lattice cube dimension" in r.stdout
+        assert "-s  --stride              Specify the stride used in CSoA memory layout" in r.stdout
+
+
+@pytest.mark.parametrize("args,msg", [
+    (["-d", "-4"], "Please enter a valid lattice dimension"),
+    (["-i", "-1"], "Please enter a valid number of iterations"),
+    (["-n", "-0.5"], "Please enter a valid viscosity value"),
+    (["-s", "-2"], "Please enter a valid number for stride value"),
+    (["-D", "-1"], "Please enter a valid device"),
+])
+def test_invalid_numbers(args, msg):
+    r = _run(*args)
+    assert r.returncode == 1 and msg in r.stderr
+
+
+def test_bad_work_group_size():
+    r = _run("-d", "8", "-w", "64,64,64")
+    assert r.returncode != 0 and "Please enter a good work_group_size" in r.stderr   # lbmcl.hpp:375-378
+
+
+def test_without_gpu_the_program_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = _run("-d", "8", "-i", "2", "-e", "0")
+    assert r.returncode != 0 and "no CUDA device" in r.stderr and "no CPU path" in r.stderr
+
+
+# ---------------------------------------------------------------------------------------------- GPU
+def _read_all(results, its, every):
+    from lbmcl_b200.vti import read_vti
+    width = len(str(its))
+    return [read_vti(os.path.join(results, f"lbmcl.{it:0{width}d}.vti")) for it in range(0, its + 1, every)]
+
+
+@pytest.mark.gpu
+def test_make_test8(tmp_path):
+    """reference Makefile:73-78 + verify against the golden fixtures, then exact comparison of every
+    VTI value with the oracle."""
+    from oracle import Oracle
+    res = str(tmp_path)
+    r = subprocess.run(["make", "-C", HOST, "test8", f"RESULTS={res}", f"DUMP_PATH={res}"], stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "verify: PASS (11 iterations compared)" in r.stdout
+    for key in ("kernel options   = -DDIM=8 -DLWS=8 -DSTRIDE_DIV=3 -DSTRIDE_MOD=7 -DVISCOSITY=0.0089 -DVELOCITY=0.05 "
+                "-DFP_SINGLE", "dim              = 8", "stride           = 8", "precision        = single",
+                "   Total time: ", " Kernels time: ", "  Total MLUPS: ", "Kernels MLUPS: "):
+        assert key in r.stdout, key
+    stat = [l for l in r.stderr.splitlines() if l.count(";") == 11]
+    assert len(stat) == 1                                              # lbmcl.hpp:648-669
+    f = stat[0].split(";")
+    assert f[1:8] == ["single", "8", "10", "1", "008,008,008", "8", "0"]
+    exp = Oracle("f32").run(8, 8, 0.0089, 0.05, 10, 1)
+    for k, d in enumerate(_read_all(res, 10, 1)):
+        assert d["arrays"]["rho"].tobytes() == np.ascontiguousarray(wet(exp["rho"][k], 8)).tobytes()
+        v = np.moveaxis(wet(exp["u"][k], 8), 0, -1).reshape(-1, 3)
+        assert d["arrays"]["v"].tobytes() == np.ascontiguousarray(v).tobytes()
+
+
+@pytest.mark.gpu
+def test_make_test32(tmp_path):
+    """reference Makefile:81-86: 32^3, 500 iterations, every 20, -w 32,32,1, -s 32."""
+    res = str(tmp_path)
+    r = subprocess.run(["make", "-C", HOST, "test32", f"RESULTS={res}", f"DUMP_PATH={res}"], stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "verify: PASS (9 iterations compared)" in r.stdout
+    assert len([f for f in os.listdir(res) if f.endswith(".vti")]) == 26
+
+
+@pytest.mark.gpu
+def test_double_precision_run_matches_oracle(tmp_path):
+    from oracle import Oracle
+    res = str(tmp_path)
+    r = _run("-D", "0", "-d", "32", "-i", "10", "-e", "5", "-s", "32", "-F", "-v", res, "-p", res)
+    assert r.returncode == 0, r.stderr
+    assert "precision        = double" in r.stdout and "-DFP_DOUBLE" in r.stdout
+    exp = Oracle("f64").run(32, 32, 0.0089, 0.05, 10, 5)
+    for k, d in enumerate(_read_all(res, 10, 5)):
+        assert d["arrays"]["rho"].dtype == np.float64
+        assert d["arrays"]["rho"].tobytes() == np.ascontiguousarray(wet(exp["rho"][k], 32)).tobytes()
+
+
+def _expected_f_dump(f, dim, stride):
+    """reference lbmcl.hpp:206-258 restated in Python for the comparison"""
+    dd = len(str(dim))
+    head = " " * (dd * 3 + 5) + "".join("%8d " % q for q in range(19)) + "\n"
+    out = []
+    for z in range(dim):
+        for y in range(dim):
+            out.append(head)
+            for x in range(dim):
+                i = x + y * dim + z * dim * dim
+                vals = "".join("%8.6f " % float(f[((i // stride) * 19 + q) * stride + (i & (stride - 1))]) for q in range(19))
+                out.append("%*s%d,%d,%d) " % (dd, "(", x, y, z) + vals + "\n")
+            out.append("\n")
+        out.append("\n")
+    out.append("\n")
+    return "".join(out)
+
+
+@pytest.mark.gpu
+def test_make_testall_dumps(tmp_path):
+    """reference Makefile:66-70 (-f -m): map.dump and every f_<it>.dump against the oracle's state."""
+    from oracle import Oracle
+    res = str(tmp_path)
+    r = subprocess.run(["make", "-C", HOST, "testall", f"RESULTS={res}", "OPTIMIZE=false"], stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    dim, stride, its = 8, 8, 10
+    text = open(os.path.join(res, "map.dump")).read()
+    assert text.startswith("# FLUID       1\n# MOVING      2\n# BOUNDARY    3\n# WALL        4\n# CORNER      5\n\n")
+    rows = [l.split() for l in text.splitlines()[6:] if l.strip()]
+    got = np.array(rows, dtype=int).reshape(dim, dim, dim)
+    m = Oracle("f32").cell_map(dim).reshape(dim, dim, dim)
+    exp = np.zeros_like(m)
+    exp[m == 1] = 1
+    exp[(m & 2) != 0] = 2
+    exp[(m & 0x3f0) != 0] = 3      # lid cells carry FRONT -> 3 (lbmcl.hpp:188-193, later category wins)
+    exp[m == 8] = 4
+    exp[m == 4] = 5
+    assert np.array_equal(got, exp)
+    # testall passes -o: the fast variant is only within tolerance, so compare the dump numerically ...
+    o = Oracle("f32")
+    st = o.alloc(dim)
+    o.init(st, dim, stride, 0.0089, 0.05)
+    for it in range(0, its + 1):
+        src = st["f_collide"] if it == 0 or it % 2 == 1 else st["f_stream"]     # lbmcl.hpp:503, 517-519
+        lines = open(os.path.join(res, f"f_{it:02d}.dump")).read()
+        exp_text = _expected_f_dump(src, dim, stride)
+        assert len(lines) == len(exp_text)
+        g = np.array([float(t) for l in lines.splitlines() if l.lstrip().startswith("(") for t in l.split()[1:]])
+        e = np.array([float(t) for l in exp_text.splitlines() if l.lstrip().startswith("(") for t in l.split()[1:]])
+        assert np.array_equal(np.isnan(g), np.isnan(e))
+        assert np.nanmax(np.abs(g - e)) <= 2e-6
+        if it >= 1:
+            o.step(st, dim, stride, 0.0089, 0.05, it, 1)
+    # ... and byte for byte with the strict kernels
+    res2 = str(tmp_path / "strict")
+    os.makedirs(res2)
+    r = _run("-D", "0", "-d", "8", "-i", "3", "-e", "1", "-s", "8", "-v", res2, "-p", res2, "-f", "-m")
+    assert r.returncode == 0, r.stderr
+    st = o.alloc(dim)
+    o.init(st, dim, stride, 0.0089, 0.05)
+    for it in range(0, 4):
+        src = st["f_collide"] if it == 0 or it % 2 == 1 else st["f_stream"]
+        assert open(os.path.join(res2, f"f_{it}.dump")).read() == _expected_f_dump(src, dim, stride), it
+        if it >= 1:
+            o.step(st, dim, stride, 0.0089, 0.05, it, 1)
