@@ -46,7 +46,7 @@ typedef enum lbm_precision { LBM_F32 = 0, LBM_F64 = 1 } lbm_precision;
 
 /* Kernel organisation.  All variants compute the same function. */
 typedef enum lbm_variant {
-    LBM_VARIANT_AUTO = 0,   /* widest vector variant the stride allows                          */
+    LBM_VARIANT_AUTO = 0,   /* the fastest measured on B200: currently the scalar variant        */
     LBM_VARIANT_SCALAR = 1, /* two-lattice pull, one cell per thread                             */
     LBM_VARIANT_VEC2 = 2,   /* two-lattice pull, 2 cells per thread, x shifts by warp shuffle    */
     LBM_VARIANT_VEC4 = 4    /* two-lattice pull, 4 cells per thread (128-bit fp32 access)        */
@@ -67,14 +67,15 @@ typedef struct lbm_params {
                               6-significant-digit text round trip (lbmcl.hpp:140-141)   */
     double velocity;       /* lid speed, same round trip                                            */
     int64_t stride;        /* CSoA stride, power of two, 1 .. DIM^3 (-s; lbmcl.hpp:384-387)         */
-    int32_t block_x;       /* requested work-group shape (-w; lbmcl.hpp:371-382); a hint: the       */
-    int32_t block_y;       /*   library clamps it to a legal CUDA block (see lbm_block_shape)       */
+    int32_t block_x;       /* requested work-group shape (-w; lbmcl.hpp:371-382); a hint: by        */
+    int32_t block_y;       /*   default the library uses x-major rows (see lbm_block_shape)         */
     int32_t block_z;
     int32_t device;        /* CUDA ordinal (-D); <0 = current device                                */
     int32_t variant;       /* lbm_variant                                                           */
     int32_t z_begin;       /* owned global planes [z_begin, z_end); 0, DIM for a single device      */
     int32_t z_end;
-    int32_t reserved[8];   /* must be zero                                                          */
+    int32_t reserved[8];   /* zero, except the tuning/test hooks: [0] = 1 forces the generic CSoA
+                              addressing, [1] = 1 honours block_x/y/z exactly                        */
 } lbm_params;
 
 typedef struct lbm_ctx lbm_ctx;

@@ -287,23 +287,38 @@ int compute_stale(lbm_ctx *c, const Consts<T> &k, T (&stale)[2][Q])
     return LBM_OK;
 }
 
-// Choose the CUDA block from the requested work-group shape: powers of two, bx*VEC | DIM, by | DIM,
-// at most 256 threads (the kernels are compiled with __launch_bounds__(256)).
+// CUDA block of the step kernel.  Constraints: powers of two, bx*VEC | DIM, by | DIM, at most 256
+// threads (the kernels are compiled with __launch_bounds__(256)).
+//   default            x-major rows: bx = min(DIM/VEC, 256), the rest of the 256 threads in y, then z.
+//                      Measured on B200 (profiles/r01_sweep.md): whole x-rows per block are never worse
+//                      than any other shape, and shapes with a short x extent (the reference default
+//                      -w 8,8,8) lose coalescing.  The requested work-group size is therefore a hint
+//                      that does not change the shape -- it never changes the results either.
+//   reserved[1] == 1   honour the requested shape as far as the constraints allow (sweeps, tests).
 void choose_block(lbm_ctx *c)
 {
     const int dim = c->dim;
-    int bx = floor_pow2(c->p.block_x > 0 ? c->p.block_x : 1) / c->vec;
-    if (bx < 1) bx = 1;
-    if (bx > dim / c->vec) bx = dim / c->vec;
-    int by = floor_pow2(c->p.block_y > 0 ? c->p.block_y : 1);
-    if (by > dim) by = dim;
-    int bz = floor_pow2(c->p.block_z > 0 ? c->p.block_z : 1);
-    if (bz > dim) bz = dim;
-    if (bz > 64) bz = 64;
-    while (bx * by * bz > 256) {
-        if (bz > 1) bz /= 2;
-        else if (by > 1) by /= 2;
-        else bx /= 2;
+    int bx, by, bz;
+    if (c->p.reserved[1] == 1) {
+        bx = floor_pow2(c->p.block_x > 0 ? c->p.block_x : 1) / c->vec;
+        if (bx < 1) bx = 1;
+        if (bx > dim / c->vec) bx = dim / c->vec;
+        by = floor_pow2(c->p.block_y > 0 ? c->p.block_y : 1);
+        if (by > dim) by = dim;
+        bz = floor_pow2(c->p.block_z > 0 ? c->p.block_z : 1);
+        if (bz > dim) bz = dim;
+        if (bz > 64) bz = 64;
+        while (bx * by * bz > 256) {
+            if (bz > 1) bz /= 2;
+            else if (by > 1) by /= 2;
+            else bx /= 2;
+        }
+    } else {
+        bx = dim / c->vec < 256 ? dim / c->vec : 256;
+        by = 256 / bx < dim ? 256 / bx : dim;
+        bz = 256 / (bx * by) < dim ? 256 / (bx * by) : dim;
+        if (bz > 64) bz = 64;
+        if (bz < 1) bz = 1;
     }
     c->block = dim3(bx, by, bz);
 }
@@ -442,9 +457,13 @@ int lbm_create(const lbm_params *p, lbm_ctx **out)
     else c->layout_mode = LM_GENERIC;
     if (p->reserved[0] == 1) c->layout_mode = LM_GENERIC;  // test hook: force the generic addressing
 
-    // widest vector the stride, the row length and the precision allow (16-byte accesses)
+    // AUTO = one cell per thread.  Measured on B200 (profiles/): with 40-48 registers the scalar kernel
+    // keeps 40+ warps per SM in flight and every warp request is already a full 128-byte line, so it
+    // sustains 6.5-6.9 TB/s; the 2- and 4-cell variants (64- and 128-bit accesses, x shifts by warp
+    // shuffle) need 64-150 registers, drop to 16-24 warps per SM and are 3-8 % slower.  They stay
+    // selectable.  Vector width is limited to 16-byte accesses inside one CSoA run.
     const int vmax = p->precision == LBM_F32 ? 4 : 2;
-    int vec = p->variant == LBM_VARIANT_AUTO ? vmax : (p->variant == LBM_VARIANT_SCALAR ? 1 : p->variant);
+    int vec = (p->variant == LBM_VARIANT_AUTO || p->variant == LBM_VARIANT_SCALAR) ? 1 : p->variant;
     if (vec > vmax) vec = vmax;
     while (vec > 1 && (p->stride % vec != 0 || p->dim % vec != 0)) vec /= 2;
     c->vec = vec;

@@ -82,9 +82,24 @@ def test_block_shapes(block):
     """-w is a hint: any requested work-group shape gives the same result."""
     dim, stride, nu, u_lid, its, every = 32, 32, 0.0089, 0.05, 6, 2
     exp = Oracle("f32").run(dim, stride, nu, u_lid, its, every)
-    with _sim(dim=dim, stride=stride, block=block) as s:
-        rho, u = s.run_snapshots(its, every)
-    assert rho.tobytes() == exp["rho"].tobytes() and u.tobytes() == exp["u"].tobytes()
+    for variant in (1, 2, 4):
+        with _sim(dim=dim, stride=stride, block=block, exact_block=True, variant=variant) as s:
+            rho, u = s.run_snapshots(its, every)
+        assert rho.tobytes() == exp["rho"].tobytes() and u.tobytes() == exp["u"].tobytes()
+    with _sim(dim=dim, stride=stride, block=block) as s:   # default: the hint does not change the shape
+        assert s.block_shape == ((32, 8, 1), 1)
+
+
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+@pytest.mark.parametrize("variant", [1, 2, 4])
+def test_generic_addressing_equals_fast_addressing(variant, precision):
+    """LM_GENERIC (any stride) and LM_ROWS / LM_SOA (uniform offsets) are the same function."""
+    dim, its, every = 32, 6, 3
+    for stride in (32, 8, 32768):
+        exp = Oracle(precision).run(dim, stride, 0.0089, 0.05, its, every)
+        with _sim(dim=dim, precision=precision, stride=stride, variant=variant, generic_addressing=True) as s:
+            rho, u = s.run_snapshots(its, every)
+        assert rho.tobytes() == exp["rho"].tobytes() and u.tobytes() == exp["u"].tobytes()
 
 
 def test_step_api_equals_run_api():
@@ -235,3 +250,20 @@ def test_dense_halo_transport_matches_single():
     lo.close()
     hi.close()
     assert rho.tobytes() == exp["rho"][1].tobytes() and u.tobytes() == exp["u"][1].tobytes()
+
+
+def test_slab_group_across_devices_matches_single():
+    """Same-process group with one slab per physical GPU: the crossing populations travel as peer
+    (NVLink) stores from inside the boundary-plane kernel.  Needs >= 2 GPUs (gpurun --gpus N)."""
+    import torch
+    from lbmcl_b200.capi import Group
+    n_dev = torch.cuda.device_count()
+    if n_dev < 2:
+        pytest.skip("one GPU only")
+    for precision, dim, stride, its, every in (("f32", 32, 32, 12, 4), ("f64", 64, 64, 8, 4)):
+        exp = Oracle(precision).run(dim, stride, 0.0089, 0.05, its, every)
+        for n in sorted({2, n_dev}):
+            with Group(list(range(n)), dim=dim, precision=precision, stride=stride) as g:
+                rho, u = g.run_snapshots(its, every)
+            assert rho.tobytes() == exp["rho"].tobytes(), (precision, n)
+            assert u.tobytes() == exp["u"].tobytes(), (precision, n)

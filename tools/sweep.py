@@ -32,7 +32,7 @@ def main():
         block = tuple(int(v) for v in blk.split(","))
         try:
             with Simulation(dim=a.dim, precision=a.precision, stride=stride, block=block, variant=variant,
-                            fast_math=bool(fast)) as s:
+                            fast_math=bool(fast), exact_block=True) as s:
                 s.init()
                 s.run(10, 0)
                 s.sync()
