@@ -63,6 +63,9 @@ struct StepArgs {
     //   soff[q]  from the address of (x, y, z, 0) to the address of (x, y, z, q)
     long long goff[Q];
     long long soff[Q];
+    // AA variant, SHIFT step: from the address of (x + ex, y, z, 0) to the address of
+    // (x + ex, y + ey, z + ez, q)
+    long long poff[Q];
 };
 
 // How neighbour addresses are formed (chosen by the host from stride and DIM):
@@ -408,6 +411,183 @@ __global__ void __launch_bounds__(256) step_pull_kernel(const StepArgs<T> a)
             *reinterpret_cast<V *>(a.u + 2 * a.n_local + id0) = vz;
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// In-place AA-pattern variant (Bailey et al. 2009): ONE lattice, half the memory of the two-lattice
+// scheme, same 19 loads + 19 stores per cell.  Iterations alternate between
+//   LOCAL step (1st, 3rd, ..):  read the cell's own 19 slots (the lattice is in the reference's
+//                               pre-collision form S), collide, store f'_q into the cell's slot opp(q);
+//   SHIFT step (2nd, 4th, ..):  f_q = A(c - e_q, opp(q)), collide, store f'_q into A(c + e_q, q),
+//                               which leaves the lattice in the S form again.
+// In either step a thread reads and writes exactly the same 19 slots, so the update is race free.
+// Populations that would arrive from a WALL cell are never-written slots in the reference:
+// here they are replaced explicitly by their initial value (the `stale` constants) using the cell's
+// side bits, for all six walls.
+template <typename T, bool FAST, bool MACRO, bool SHIFT, int LM>
+__global__ void __launch_bounds__(256) step_aa_kernel(const StepArgs<T> a)
+{
+    const int dim = a.dim;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int z = a.z_begin + blockIdx.z * blockDim.z + threadIdx.z;
+    if (z >= a.z_end) return;
+    const int rowbits = row_bits(y, z, dim);
+    if (rowbits == CT_WALL || x == 0 || x >= dim - 1) return;  // WALL cells neither read nor write
+
+    const long long plane = (long long)dim * dim;
+    const long long id0 = x + (long long)y * dim + (long long)(z - a.zs0) * plane;
+    const long long qp = a.lay.qpitch();
+    T *const lat = a.dst;
+
+    long long b0, bm = 0, bp = 0;
+    if constexpr (LM == LM_ROWS) {
+        const long long rowbase = ((long long)y * dim + (long long)(z - a.zs0) * plane) * Q;
+        const int sm = (int)a.lay.smod;
+        b0 = rowbase + ((((x >> a.lay.sdiv) * Q) << a.lay.sdiv) + (x & sm));
+        if constexpr (SHIFT) {
+            bm = rowbase + (((((x - 1) >> a.lay.sdiv) * Q) << a.lay.sdiv) + ((x - 1) & sm));
+            bp = rowbase + (((((x + 1) >> a.lay.sdiv) * Q) << a.lay.sdiv) + ((x + 1) & sm));
+        }
+    } else if constexpr (LM == LM_SOA) {
+        b0 = id0;
+        bm = id0 - 1;
+        bp = id0 + 1;
+    } else {
+        b0 = a.lay.base(id0);
+    }
+    char *const c0 = reinterpret_cast<char *>(lat + b0);
+    char *const cm = reinterpret_cast<char *>(lat + bm);
+    char *const cp = reinterpret_cast<char *>(lat + bp);
+
+    // where population q of this cell is read from / written to
+    auto slot = [&](auto qc, bool for_store) -> T * {
+        constexpr int q = decltype(qc)::value;
+        if constexpr (!SHIFT) {
+            // LOCAL: read slot q, write slot opp(q), both in this cell
+            return reinterpret_cast<T *>(c0 + (for_store ? a.soff[opp(q)] : a.soff[q]));
+        } else if constexpr (LM == LM_GENERIC) {
+            const long long nid = for_store
+                ? id0 + ex(q) + (long long)ey(q) * dim + (long long)ez(q) * plane
+                : id0 - ex(q) - (long long)ey(q) * dim - (long long)ez(q) * plane;
+            return lat + a.lay.base(nid) + (for_store ? q : opp(q)) * qp;
+        } else {
+            // SHIFT: read (c - e_q, opp(q)), write (c + e_q, q): the same address for q and opp(q) swapped
+            if (for_store) return reinterpret_cast<T *>((ex(q) == 0 ? c0 : (ex(q) == 1 ? cp : cm)) + a.poff[q]);
+            return reinterpret_cast<T *>((ex(q) == 0 ? c0 : (ex(q) == 1 ? cm : cp)) + a.goff[q]);
+        }
+    };
+
+    T f[Q];
+    static_for<Q>([&](auto qc) { f[decltype(qc)::value] = *slot(qc, false); });
+
+    // raw side bits (before the CORNER / MOVING rewriting of get_cell_type)
+    int side = rowbits;
+    if (x == 1) side |= CT_LEFT;
+    if (x == dim - 2) side |= CT_RIGHT;
+    if (side != CT_NONE) {
+        const int lid = (side & CT_FRONT) ? 1 : 0;
+        static_for<Q>([&](auto qc) {
+            constexpr int q = decltype(qc)::value;
+            constexpr int from_wall = (ex(q) == 1 ? CT_LEFT : 0) | (ex(q) == -1 ? CT_RIGHT : 0) |
+                                      (ey(q) == 1 ? CT_BOTTOM : 0) | (ey(q) == -1 ? CT_TOP : 0) |
+                                      (ez(q) == 1 ? CT_BACK : 0) | (ez(q) == -1 ? CT_FRONT : 0);
+            if constexpr (from_wall != 0) {
+                if (side & from_wall) f[q] = a.stale[lid][q];
+            }
+        });
+    }
+
+    const int t = cell_type_from_row(rowbits, x, dim);
+    const T nan = static_cast<T>(__int_as_float(0x7fc00000));
+    T rho = nan, ux = nan, uy = nan, uz = nan;
+    if (t == CT_FLUID) {
+        collide_fluid<T, FAST>(f, a.c, rho, ux, uy, uz);
+    } else if (t & CT_MOVING) {
+        collide_lid<T, FAST>(f, a.c, rho);
+        ux = a.c.u_lid;
+        uy = T(0);
+        uz = T(0);
+    } else if (is_bounceback(t)) {
+        bounce_back<T>(f);
+    }
+
+    static_for<Q>([&](auto qc) { *slot(qc, true) = f[decltype(qc)::value]; });
+
+    if constexpr (MACRO) {
+        if (is_collision(t)) {
+            a.rho[id0] = rho;
+            a.u[id0] = ux;
+            a.u[a.n_local + id0] = uy;
+            a.u[2 * a.n_local + id0] = uz;
+        }
+    }
+}
+
+// `initialize` for the AA variant: the lattice starts in the reference's own form,
+// A(c, q) = f_eq_q(1, u0(c)) (kernels.cl:303-317); rho/u as in init_kernel.
+template <typename T>
+__global__ void __launch_bounds__(256) init_aa_kernel(const InitArgs<T> a)
+{
+    const int dim = a.dim;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int zl = blockIdx.z * blockDim.z + threadIdx.z;
+    if (x >= dim || y >= dim || zl >= a.nz_local) return;
+    const int z = a.zs0 + zl;
+    const long long id = x + (long long)y * dim + (long long)zl * dim * dim;
+    const int t = cell_type(x, y, z, dim);
+    const bool keep = is_collision(t);
+    const T nan = static_cast<T>(__int_as_float(0x7fc00000));
+    const T ux0 = has_front_bit(x, y, z, dim) ? a.c.u_lid : T(0);
+    a.rho[id] = keep ? T(1) : nan;
+    a.u[id] = keep ? ux0 : nan;
+    a.u[a.n_local + id] = keep ? T(0) : nan;
+    a.u[2 * a.n_local + id] = keep ? T(0) : nan;
+    const long long b = a.lay.base(id);
+    const long long qp = a.lay.qpitch();
+    static_for<Q>([&](auto qc) {
+        constexpr int q = decltype(qc)::value;
+        a.f0[b + q * qp] = init_feq<T, q>(a.c, ux0);
+    });
+}
+
+// Reference view of the AA lattice (for -f): `swapped` != 0 after a LOCAL step (slot opp(q) of the
+// source cell holds the value), 0 when the lattice is in S form.
+template <typename T>
+__global__ void __launch_bounds__(256) reference_view_aa_kernel(const T *__restrict__ lat, T *__restrict__ out,
+                                                                int dim, Layout lay, Consts<T> c, int swapped,
+                                                                int pristine)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int z = blockIdx.z * blockDim.z + threadIdx.z;
+    if (x >= dim || y >= dim || z >= dim) return;
+    const long long plane = (long long)dim * dim;
+    const long long gid = x + (long long)y * dim + (long long)z * plane;
+    const int t = cell_type(x, y, z, dim);
+    const T nan = static_cast<T>(__int_as_float(0x7fc00000));
+    const T ux0 = has_front_bit(x, y, z, dim) ? c.u_lid : T(0);
+    static_for<Q>([&](auto qc) {
+        constexpr int q = decltype(qc)::value;
+        const int sx = x - ex(q), sy = y - ey(q), sz = z - ez(q);
+        const bool inside = sx >= 0 && sx < dim && sy >= 0 && sy < dim && sz >= 0 && sz < dim;
+        const bool src_live = inside && cell_type(sx, sy, sz, dim) != CT_WALL;
+        T v;
+        if (src_live && !(pristine && t == CT_WALL)) {
+            if (swapped) {
+                const long long sid = sx + (long long)sy * dim + (long long)sz * plane;
+                v = lat[lay.base(sid) + opp(q) * lay.qpitch()];
+            } else {
+                v = lat[lay.base(gid) + q * lay.qpitch()];
+            }
+        } else if (t == CT_WALL) {
+            v = nan;
+        } else {
+            v = init_feq<T, q>(c, ux0);
+        }
+        out[lay.base(gid) + q * lay.qpitch()] = v;
+    });
 }
 
 // Cell-type map (kernels.cl:290), only for the -m dump.
