@@ -49,7 +49,9 @@ typedef enum lbm_variant {
     LBM_VARIANT_AUTO = 0,   /* the fastest measured on B200: currently the scalar variant        */
     LBM_VARIANT_SCALAR = 1, /* two-lattice pull, one cell per thread                             */
     LBM_VARIANT_VEC2 = 2,   /* two-lattice pull, 2 cells per thread, x shifts by warp shuffle    */
-    LBM_VARIANT_VEC4 = 4    /* two-lattice pull, 4 cells per thread (128-bit fp32 access)        */
+    LBM_VARIANT_VEC4 = 4,   /* two-lattice pull, 4 cells per thread (128-bit fp32 access)        */
+    LBM_VARIANT_AA = 8      /* in-place AA pattern: ONE lattice (half the memory), one cell per
+                               thread; whole cube on one device only                             */
 } lbm_variant;
 
 /*

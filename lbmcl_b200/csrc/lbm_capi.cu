@@ -46,6 +46,7 @@ struct lbm_ctx {
     long long n_alloc = 0;       // stored cells rounded up to a multiple of the stride
     Layout lay{};
     int layout_mode = LM_GENERIC;
+    bool aa = false;             // in-place AA variant: only f[0] exists
     int vec = 1;
     dim3 block{1, 1, 1};
     size_t esize = 4;
@@ -194,9 +195,20 @@ StepArgs<T> make_step_args(lbm_ctx *c, int z_begin, int z_end, const Consts<T> &
     for (int q = 0; q < Q; ++q) {
         a.soff[q] = q * S * es;
         const long long dcell = (long long)ey(q) * dim + (long long)ez(q) * plane;  // cells between the two rows
-        if (c->layout_mode == LM_ROWS) a.goff[q] = (q * S - Q * dcell) * es;
-        else if (c->layout_mode == LM_SOA) a.goff[q] = (q * S - dcell) * es;
-        else a.goff[q] = 0;
+        const long long rowmul = c->layout_mode == LM_ROWS ? Q : 1;                  // CSoA rows hold Q values per cell
+        if (c->layout_mode == LM_GENERIC) {
+            a.goff[q] = a.poff[q] = 0;
+        } else if (c->aa) {
+            a.goff[q] = (opp(q) * S - rowmul * dcell) * es;  // SHIFT step: read (c - e_q, opp(q))
+            a.poff[q] = (q * S + rowmul * dcell) * es;       //             write (c + e_q, q)
+        } else {
+            a.goff[q] = (q * S - rowmul * dcell) * es;
+            a.poff[q] = 0;
+        }
+    }
+    if (c->aa) {
+        a.dst = static_cast<T *>(c->f[0]);
+        a.src = static_cast<const T *>(c->f[0]);
     }
     return a;
 }
@@ -229,11 +241,41 @@ cudaError_t launch_step_t(lbm_ctx *c, const StepArgs<T> &a, bool macro, bool pee
     return cudaGetLastError();
 }
 
+// AA variant: iteration `it` (1-based) is a LOCAL step when odd, a SHIFT step when even.
+template <typename T>
+cudaError_t launch_aa_t(lbm_ctx *c, const StepArgs<T> &a, bool macro, cudaStream_t s)
+{
+    const int nz = a.z_end - a.z_begin;
+    if (nz <= 0) return cudaSuccess;
+    const dim3 b = c->block;
+    const dim3 g((unsigned)(c->dim / b.x), (unsigned)(c->dim / b.y), (unsigned)((nz + b.z - 1) / b.z));
+    const bool fast = c->p.fast_math != 0;
+    const bool shift = ((c->iteration + 1) % 2) == 0;
+#define LBM_AA_LM(F, M, SH)                                                                       \
+    do {                                                                                          \
+        if (c->layout_mode == LM_ROWS) step_aa_kernel<T, F, M, SH, LM_ROWS><<<g, b, 0, s>>>(a);   \
+        else if (c->layout_mode == LM_SOA) step_aa_kernel<T, F, M, SH, LM_SOA><<<g, b, 0, s>>>(a); \
+        else step_aa_kernel<T, F, M, SH, LM_GENERIC><<<g, b, 0, s>>>(a);                          \
+    } while (0)
+#define LBM_AA(F, M)                           \
+    do {                                       \
+        if (shift) LBM_AA_LM(F, M, true);      \
+        else LBM_AA_LM(F, M, false);           \
+    } while (0)
+    if (fast) { if (macro) LBM_AA(true, true); else LBM_AA(true, false); }
+    else      { if (macro) LBM_AA(false, true); else LBM_AA(false, false); }
+#undef LBM_AA
+#undef LBM_AA_LM
+    c->launches += 1;
+    return cudaGetLastError();
+}
+
 template <typename T>
 cudaError_t launch_step_p(lbm_ctx *c, int z_begin, int z_end, bool macro, cudaStream_t s,
                           const Consts<T> &k, const T (&stale)[2][Q])
 {
     const StepArgs<T> a = make_step_args<T>(c, z_begin, z_end, k, stale);
+    if (c->aa) return launch_aa_t<T>(c, a, macro, s);
     const bool peer = (a.peer_lo != nullptr && z_begin <= c->z_begin && c->z_begin < z_end) ||
                       (a.peer_hi != nullptr && z_begin <= c->z_end - 1 && c->z_end - 1 < z_end);
     switch (c->vec) {
@@ -270,7 +312,8 @@ cudaError_t launch_init_t(lbm_ctx *c, const Consts<T> &k, cudaStream_t s)
     const int by = (256 / bx) < c->dim ? (256 / bx) : c->dim;
     const dim3 b(bx, by, 1);
     const dim3 g(c->dim / bx, c->dim / by, c->nz_local);
-    init_kernel<T><<<g, b, 0, s>>>(a);
+    if (c->aa) init_aa_kernel<T><<<g, b, 0, s>>>(a);
+    else init_kernel<T><<<g, b, 0, s>>>(a);
     return cudaGetLastError();
 }
 
@@ -408,6 +451,10 @@ int lbm_create(const lbm_params *p, lbm_ctx **out)
         return fail(nullptr, LBM_ERR_INVALID, "lbm_create: bad z range [%d, %d)", zb, ze);
     switch (p->variant) {
         case LBM_VARIANT_AUTO: case LBM_VARIANT_SCALAR: case LBM_VARIANT_VEC2: case LBM_VARIANT_VEC4: break;
+        case LBM_VARIANT_AA:
+            if (zb != 0 || ze != p->dim)
+                return fail(nullptr, LBM_ERR_INVALID, "lbm_create: the AA variant needs the whole cube on one device");
+            break;
         default: return fail(nullptr, LBM_ERR_INVALID, "lbm_create: unknown variant %d", p->variant);
     }
 
@@ -464,6 +511,8 @@ int lbm_create(const lbm_params *p, lbm_ctx **out)
     // selectable.  Vector width is limited to 16-byte accesses inside one CSoA run.
     const int vmax = p->precision == LBM_F32 ? 4 : 2;
     int vec = (p->variant == LBM_VARIANT_AUTO || p->variant == LBM_VARIANT_SCALAR) ? 1 : p->variant;
+    c->aa = p->variant == LBM_VARIANT_AA;
+    if (c->aa) vec = 1;
     if (vec > vmax) vec = vmax;
     while (vec > 1 && (p->stride % vec != 0 || p->dim % vec != 0)) vec /= 2;
     c->vec = vec;
@@ -489,7 +538,7 @@ int lbm_create(const lbm_params *p, lbm_ctx **out)
 
     const size_t f_bytes = (size_t)c->n_alloc * Q * c->esize;
     const size_t m_bytes = (size_t)c->n_local * c->esize;
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < (c->aa ? 1 : 2); ++i) {
         cudaError_t err = cudaMalloc(&c->f[i], f_bytes);
         if (cuda_or_bail(err, "cudaMalloc(f)")) return bail(err == cudaErrorMemoryAllocation ? LBM_ERR_OOM : LBM_ERR_CUDA);
         c->device_bytes += (int64_t)f_bytes;
@@ -681,7 +730,15 @@ int lbm_read_f(lbm_ctx *c, void *f_host)
     const int by = (256 / bx) < c->dim ? (256 / bx) : c->dim;
     const dim3 b(bx, by, 1), g(c->dim / bx, c->dim / by, c->dim);
     const int pristine = c->iteration == 0 ? 1 : 0;
-    if (c->p.precision == LBM_F32)
+    if (c->aa) {
+        const int swapped = (c->iteration % 2) == 1 ? 1 : 0;
+        if (c->p.precision == LBM_F32)
+            reference_view_aa_kernel<float><<<g, b, 0, c->stream>>>((const float *)c->f[0], (float *)d, c->dim, c->lay,
+                                                                    c->cf, swapped, pristine);
+        else
+            reference_view_aa_kernel<double><<<g, b, 0, c->stream>>>((const double *)c->f[0], (double *)d, c->dim,
+                                                                     c->lay, c->cd, swapped, pristine);
+    } else if (c->p.precision == LBM_F32)
         reference_view_kernel<float><<<g, b, 0, c->stream>>>((const float *)c->f[c->cur], (float *)d, c->dim, c->zs0,
                                                              c->nz_local, 0, c->dim, c->lay, c->lay, c->cf, pristine);
     else
@@ -759,6 +816,7 @@ int lbm_step_planes(lbm_ctx *c, int z_begin, int z_end, int update_macro)
 {
     if (!c) return LBM_ERR_INVALID;
     if (!c->initialised) return fail(c, LBM_ERR_STATE, "lbm_step_planes before lbm_init");
+    if (c->aa) return fail(c, LBM_ERR_INVALID, "lbm_step_planes: not available with the AA variant");
     if (z_begin < c->z_begin || z_end > c->z_end || z_begin > z_end)
         return fail(c, LBM_ERR_INVALID, "lbm_step_planes: [%d, %d) outside the owned planes [%d, %d)", z_begin,
                     z_end, c->z_begin, c->z_end);

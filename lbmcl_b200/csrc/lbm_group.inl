@@ -78,6 +78,8 @@ int lbm_group_create(const lbm_params *p, const int32_t *devices, int n, lbm_gro
     if (!out) return gfail(nullptr, LBM_ERR_INVALID, "lbm_group_create: out is NULL");
     *out = nullptr;
     if (!p || !devices || n < 1) return gfail(nullptr, LBM_ERR_INVALID, "lbm_group_create: bad arguments");
+    if (p->variant == LBM_VARIANT_AA && n > 1)
+        return gfail(nullptr, LBM_ERR_INVALID, "lbm_group_create: the AA variant is single-device");
     if (p->dim < 4 || (p->dim % n) != 0 || p->dim / n < 1)
         return gfail(nullptr, LBM_ERR_INVALID, "lbm_group_create: dim %d is not divisible into %d z-slabs", p->dim, n);
     lbm_group *g = new (std::nothrow) lbm_group();

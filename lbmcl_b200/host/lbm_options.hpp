@@ -5,7 +5,8 @@
 //   -P platform (accepted, ignored: there is no OpenCL platform)   -D device = CUDA ordinal
 //   -d dim  -n viscosity  -u velocity  -i iterations  -e every  -w x,y,z  -s stride
 //   -F double  -o optimize  -v vtk_path  -p dump_path  -m dump_map  -f dump_f  -h help
-// plus one new option, -G / --gpus N: split the cube into N z-slabs over N devices.
+// plus two new options: -G / --gpus N splits the cube into N z-slabs over N devices, and
+// -A / --aa selects the in-place AA-pattern kernels (one lattice, half the device memory).
 // Unknown options and -h print the help and exit with status 1; an invalid number prints the
 // reference's message for that option and exits with status 1.
 #pragma once
@@ -36,6 +37,7 @@ struct lbm_options {
     bool dump_map = false;
     bool dump_f = false;
     int gpus = 1;
+    bool aa = false;
 
     static void print_help()
     {
@@ -56,6 +58,7 @@ struct lbm_options {
             "-m  --dump_map            Dump the lattice map                           ",
             "-f  --dump_f              Dump the lattice \"f\" for each iteration      ",
             "-G  --gpus                Split the cube into z-slabs over N GPUs        ",
+            "-A  --aa                  Use the in-place AA-pattern kernels            ",
             "-h  --help                Show this help message and exit                ",
         };
         for (const char *l : lines) std::cout << l << "\n";
@@ -85,10 +88,11 @@ struct lbm_options {
             {"optimize", no_argument, nullptr, 'o'},         {"vtk_path", required_argument, nullptr, 'v'},
             {"dump_path", required_argument, nullptr, 'p'},  {"dump_map", no_argument, nullptr, 'm'},
             {"dump_f", no_argument, nullptr, 'f'},           {"gpus", required_argument, nullptr, 'G'},
-            {"help", no_argument, nullptr, 'h'},             {nullptr, 0, nullptr, 0}};
+            {"aa", no_argument, nullptr, 'A'},               {"help", no_argument, nullptr, 'h'},
+            {nullptr, 0, nullptr, 0}};
         opterr = 0;
         int opt;
-        while ((opt = getopt_long(argc, argv, "P:D:d:n:u:i:e:v:w:s:Fop:mfhG:", long_opts, nullptr)) >= 0) {
+        while ((opt = getopt_long(argc, argv, "P:D:d:n:u:i:e:v:w:s:Fop:mfhG:A", long_opts, nullptr)) >= 0) {
             switch (opt) {
                 case 'P': platformID = (int)parse_count(optarg, "Please enter a valid platform"); break;
                 case 'D': deviceID = (int)parse_count(optarg, "Please enter a valid device"); break;
@@ -128,6 +132,7 @@ struct lbm_options {
                     break;
                 case 'm': dump_map = true; break;
                 case 'f': dump_f = true; break;
+                case 'A': aa = true; break;
                 case 'G': gpus = (int)parse_count(optarg, "Please enter a valid number of GPUs"); break;
                 default: print_help(); break;  // 'h', '?'
             }

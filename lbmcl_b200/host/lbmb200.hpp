@@ -54,6 +54,7 @@ class LBMCL {
     bool dump_f;
     bool dump_data;
     int gpus;
+    bool aa;
 
     lbm_ctx *ctx = nullptr;
     lbm_group *group = nullptr;
@@ -104,6 +105,7 @@ class LBMCL {
         if (optimize) o << "-use_fast_math ";
         o << "[sm_100a";
         if (gpus > 1) o << ", " << gpus << " z-slabs";
+        if (aa) o << ", in-place AA";
         o << "]";
         return o.str();
     }
@@ -266,10 +268,10 @@ class LBMCL {
 public:
     LBMCL(size_t dim, T viscosity, T velocity, size_t iterations, size_t every, std::string vtk_path = "",
           size_t lwx = 1, size_t lwy = 1, size_t lwz = 1, size_t stride = 32, bool optimize = true,
-          std::string dump_path = "", bool dump_map = false, bool dump_f = false, int gpus = 1)
+          std::string dump_path = "", bool dump_map = false, bool dump_f = false, int gpus = 1, bool aa = false)
         : dim(dim), viscosity(viscosity), velocity(velocity), iterations(iterations), every(every),
           vtk_path(std::move(vtk_path)), stride(stride), optimize(optimize), dump_path(std::move(dump_path)),
-          dump_map(dump_map), dump_f(dump_f), dump_data(every != 0), gpus(gpus < 1 ? 1 : gpus)
+          dump_map(dump_map), dump_f(dump_f), dump_data(every != 0), gpus(gpus < 1 ? 1 : gpus), aa(aa)
     {
         if (!is_pow2(this->dim)) {  // lbmcl.hpp:364-367
             this->dim = floor_pow2(this->dim);
@@ -312,7 +314,7 @@ public:
         p.block_y = (int32_t)lws[1];
         p.block_z = (int32_t)lws[2];
         p.device = deviceID < 0 ? 0 : deviceID;
-        p.variant = LBM_VARIANT_AUTO;
+        p.variant = aa ? LBM_VARIANT_AA : LBM_VARIANT_AUTO;
         if (const char *v = std::getenv("LBM_VARIANT")) p.variant = std::atoi(v);
         char name[256] = "?";
         if (gpus > 1) {

@@ -10,7 +10,7 @@ template <typename T>
 static void run(const lbm_options &o)
 {
     LBMCL<T> sim(o.dim, (T)o.viscosity, (T)o.velocity, o.iterations, o.every, o.vtk_path, o.lwx, o.lwy, o.lwz,
-                 o.stride, o.optimize, o.dump_path, o.dump_map, o.dump_f, o.gpus);
+                 o.stride, o.optimize, o.dump_path, o.dump_map, o.dump_f, o.gpus, o.aa);
     sim.setupSimulation(o.platformID, o.deviceID);
     sim.printConfiguration();
     sim.performSimulation();

@@ -50,7 +50,7 @@ CASES = [
 
 
 @pytest.mark.parametrize("precision", ["f32", "f64"])
-@pytest.mark.parametrize("variant", [0, 1, 2, 4])
+@pytest.mark.parametrize("variant", [0, 1, 2, 4, 8])
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "d%d_s%d_i%d_e%d" % (c[0], c[1], c[4], c[5]))
 def test_strict_matches_oracle(case, variant, precision):
     dim, stride, nu, u_lid, its, every = case
@@ -67,12 +67,14 @@ def test_strict_matches_oracle(case, variant, precision):
 
 
 @pytest.mark.parametrize("precision", ["f32", "f64"])
+@pytest.mark.parametrize("variant", [0, 4, 8])
 @pytest.mark.parametrize("case", CASES[:5], ids=lambda c: "d%d_s%d_i%d_e%d" % (c[0], c[1], c[4], c[5]))
-def test_fast_within_tolerance(case, precision):
+def test_fast_within_tolerance(case, variant, precision):
     """-o (contracted arithmetic, approximate fp32 division) against the strict oracle."""
     dim, stride, nu, u_lid, its, every = case
     exp = Oracle(precision).run(dim, stride, nu, u_lid, its, every)
-    with _sim(dim=dim, precision=precision, viscosity=nu, velocity=u_lid, stride=stride, fast_math=True) as s:
+    with _sim(dim=dim, precision=precision, viscosity=nu, velocity=u_lid, stride=stride, fast_math=True,
+              variant=variant) as s:
         rho, u = s.run_snapshots(its, every)
     _compare(rho, u, exp["rho"], exp["u"], u_lid, TOL[precision], exact=False)
 
@@ -91,7 +93,7 @@ def test_block_shapes(block):
 
 
 @pytest.mark.parametrize("precision", ["f32", "f64"])
-@pytest.mark.parametrize("variant", [1, 2, 4])
+@pytest.mark.parametrize("variant", [1, 2, 4, 8])
 def test_generic_addressing_equals_fast_addressing(variant, precision):
     """LM_GENERIC (any stride) and LM_ROWS / LM_SOA (uniform offsets) are the same function."""
     dim, its, every = 32, 6, 3
@@ -126,8 +128,9 @@ def test_map_matches_reference_classification():
 
 
 @pytest.mark.parametrize("precision", ["f32", "f64"])
-@pytest.mark.parametrize("its", [0, 1, 2, 5])
-def test_population_dump_view(its, precision):
+@pytest.mark.parametrize("variant", [1, 8])
+@pytest.mark.parametrize("its", [0, 1, 2, 5, 6])
+def test_population_dump_view(its, variant, precision):
     """lbm_read_f presents the lattice as the reference stores it (pre-collision, CSoA order, pushed
     values in WALL cells, never-written slots at their initial value): the -f dump (lbmcl.hpp:206-258)."""
     dim, stride, nu, u_lid = 16, 16, 0.0089, 0.05
@@ -138,7 +141,7 @@ def test_population_dump_view(its, precision):
         o.step(st, dim, stride, nu, u_lid, it, 0)
     # the buffer iteration its+1 would read (lbmcl.hpp:517-519)
     exp = st["f_stream"] if (its + 1) % 2 == 0 else st["f_collide"]
-    with _sim(dim=dim, precision=precision, stride=stride) as s:
+    with _sim(dim=dim, precision=precision, stride=stride, variant=variant) as s:
         s.init()
         s.run(its, 0)
         got = s.read_f()
@@ -267,3 +270,18 @@ def test_slab_group_across_devices_matches_single():
                 rho, u = g.run_snapshots(its, every)
             assert rho.tobytes() == exp["rho"].tobytes(), (precision, n)
             assert u.tobytes() == exp["u"].tobytes(), (precision, n)
+
+
+def test_aa_variant_uses_half_the_lattice_memory_and_matches_at_size():
+    """The in-place AA variant: one lattice instead of two, same bits as the two-lattice kernel at a
+    size where the oracle is too slow to be run for long (128^3, 40 iterations, odd and even counts)."""
+    with _sim(dim=128, stride=32, variant=1) as a, _sim(dim=128, stride=32, variant=8) as b:
+        assert b.device_bytes < 0.6 * a.device_bytes
+        for its in (40, 41):
+            a.init(); a.run(its, its); ra, ua = a.read_macros()
+            b.init(); b.run(its, its); rb, ub = b.read_macros()
+            assert ra.tobytes() == rb.tobytes() and ua.tobytes() == ub.tobytes()
+            assert a.read_f().tobytes() == b.read_f().tobytes()
+    from lbmcl_b200.capi import LbmError
+    with pytest.raises(LbmError):
+        _sim(dim=32, variant=8, z_range=(0, 16))
