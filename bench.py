@@ -9,8 +9,8 @@ defines it (lbmcl.hpp:604-620): wet cells (DIM-2)^3 x iterations / time.
 
 Workloads (BASELINE.json configs): N = 1 -> LDC 256^3 fp32 (config 3, the one the metric is quoted
 on); N = 2, 4, 8 -> LDC 1024^3 fp32 split into z-slabs (config 5; it does not fit one GPU), the five
-crossing populations per face exchanged with NCCL send/recv over NVLink, overlapped with the interior
-update.  The lattices (2.5 GB at 256^3) are far larger than the 126 MB L2, so every step streams from
+crossing populations per face exchanged with NCCL send/recv over NVLink (issued by the library on a
+high-priority stream), overlapped with the interior update.  The lattices (2.5 GB at 256^3) are far larger than the 126 MB L2, so every step streams from
 HBM; no explicit flush is needed.
 
 The JSON line also carries
@@ -217,19 +217,12 @@ class ClockSampler(threading.Thread):
 # ------------------------------------------------------------------------------------------------
 # the B200 arm
 # ------------------------------------------------------------------------------------------------
-class _DevBuf:
-    """Expose a raw device pointer to torch (zero-copy) through __cuda_array_interface__."""
-
-    def __init__(self, ptr, n, typestr):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (int(ptr), False), "version": 2}
-
-
 def run_b200(a):
     import numpy as np
     import torch
     import torch.distributed as dist
     from lbmcl_b200.capi import Simulation
-    from lbmcl_b200.slabs import exchange_halos, slab_range
+    from lbmcl_b200.slabs import slab_range
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -262,64 +255,27 @@ def run_b200(a):
     has_lo, has_hi = rank > 0, rank < world - 1
 
     if world > 1:
-        bstream = torch.cuda.Stream(device=dev, priority=-1)
-        ev_interior = torch.cuda.Event()
-        ev_boundary = torch.cuda.Event()
-        n_h = sim.halo_elems
-        ts = "<f4" if esize == 4 else "<f8"
-        send = [torch.as_tensor(_DevBuf(sim.halo_send_ptr(f), n_h, ts), device=dev) if ok else None
-                for f, ok in ((0, has_lo), (1, has_hi))]
-        recv = [torch.as_tensor(_DevBuf(sim.halo_recv_ptr(f), n_h, ts), device=dev) if ok else None
-                for f, ok in ((0, has_lo), (1, has_hi))]
-        assert all(t is None or t.dtype == tdtype for t in send)
+        # NCCL communicator owned by the library; torch.distributed only carries the 128-byte id
+        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(Simulation.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        sim.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
 
-        def one_step(macro=False):
-            # boundary planes first, on the high-priority stream
-            bstream.wait_event(ev_interior)
-            sim.set_stream(bstream.cuda_stream)
-            if has_lo:
-                sim.step_planes(z0, z0 + 1, macro)
-            if has_hi and not (has_lo and z1 - 1 == z0):
-                sim.step_planes(z1 - 1, z1, macro)
-            # the boundary kernels are done before the previous boundary event is overwritten
-            main.wait_event(ev_boundary)
-            ev_boundary.record(bstream)
-            # interior concurrently on the main stream
-            sim.set_stream(main.cuda_stream)
-            sim.step_planes(z0 + (1 if has_lo else 0), z1 - (1 if has_hi else 0), macro)
-            ev_interior.record(main)
-            sim.advance()
-            # exchange the 5 crossing populations per face (NCCL send/recv over NVLink)
-            sim.set_stream(bstream.cuda_stream)
-            sim.halo_pack()
-            with torch.cuda.stream(bstream):
-                for r in exchange_halos(send, recv, world, rank):
-                    r.wait()
-            sim.halo_unpack()
-            sim.set_stream(main.cuda_stream)
+    def run_steps(n, every=0):
+        # N = 1: n launches of the step kernel.  N > 1: per iteration boundary planes -> pack ->
+        # ncclSend/ncclRecv of the 5 crossing populations per face -> unpack on a high-priority stream,
+        # interior planes concurrently on `main` (lbm_run drives it, see include/lbm_b200.h 2b)
+        sim.run(n, every)
 
-        def run_steps(n, every=0):
-            for _ in range(n):
-                it = sim.iteration + 1
-                one_step(every != 0 and it % every == 0)
-            main.wait_stream(bstream)
-
-        def sync_all():
-            torch.cuda.synchronize(dev)
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
             dist.barrier()
-            torch.cuda.synchronize(dev)
-    else:
-        def run_steps(n, every=0):
-            sim.run(n, every)
-
-        def sync_all():
             torch.cuda.synchronize(dev)
 
     # ---- device-timed throughput: inputs resident in HBM ----
     sim.init()
-    if world > 1:
-        ev_interior.record(main)
-        ev_boundary.record(main)
     run_steps(a.warmup)
     sync_all()
     l0 = sim.launch_count
@@ -356,9 +312,6 @@ def run_b200(a):
         sync_all()
         t0 = time.perf_counter()
         sim.init()
-        if world > 1:
-            ev_interior.record(main)
-            ev_boundary.record(main)
         run_steps(a.steps, a.steps)
         sim.read_macros(rho_h, u_h)     # blocking D2H of this rank's planes into pinned memory
         sync_all()

@@ -196,6 +196,18 @@ int lbm_halo_pack(lbm_ctx *ctx);
 /* scatter the received populations into the halo planes (asynchronous, on the ctx stream) */
 int lbm_halo_unpack(lbm_ctx *ctx);
 
+/* (2b) one process per device, exchange driven by the library: the context owns an NCCL communicator
+ * over the ranks of the job (libnccl.so.2 is resolved at run time with dlopen -- the one torch already
+ * loaded under torchrun).  Rank 0 obtains an id with lbm_comm_unique_id(), the host broadcasts the 128
+ * bytes (torch.distributed, MPI, ...), every rank calls lbm_comm_init() -- a collective call.  After
+ * that lbm_run() on the slab context runs the overlapped schedule itself, per iteration: boundary planes
+ * on a high-priority stream -> pack -> ncclSend/ncclRecv of the 5 crossing populations per face ->
+ * unpack, with the interior planes concurrently on the main stream; no host synchronisation and no
+ * per-step host round trip through the caller. */
+#define LBM_COMM_ID_BYTES 128
+int lbm_comm_unique_id(uint8_t id[LBM_COMM_ID_BYTES]);
+int lbm_comm_init(lbm_ctx *ctx, const uint8_t id[LBM_COMM_ID_BYTES], int rank, int world);
+
 /* Same-process group of slab contexts, ordered by z.  lbm_group_create builds n contexts from one
  * parameter block (z range split evenly over devices[0..n-1]), enables peer access and links
  * neighbours.  The group calls mirror the single-context ones. */

@@ -6,6 +6,8 @@
 #include "../../include/lbm_b200.h"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types only: the functions are resolved with dlopen (no link-time dependency)
 
 #include <cmath>
 #include <cstdarg>
@@ -70,6 +72,14 @@ struct lbm_ctx {
     // same-process neighbours (lbm_group)
     lbm_ctx *peer[2] = {nullptr, nullptr};
 
+    // one process per device: NCCL communicator over the slabs (lbm_comm_init)
+    ncclComm_t comm = nullptr;
+    int comm_rank = -1, comm_world = 0;
+    cudaStream_t bstream = nullptr;           // high-priority stream: boundary planes + exchange
+    cudaEvent_t ev_bk[2] = {nullptr, nullptr};  // boundary kernels of iteration parity p done
+    cudaEvent_t ev_in[2] = {nullptr, nullptr};  // interior kernel of iteration parity p done
+    cudaEvent_t ev_join = nullptr;
+
     // execution
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
@@ -83,6 +93,8 @@ struct lbm_ctx {
     std::vector<EventPair> compute_events;
     double kernels_ms_accum = 0.0;  // folded-in pairs
 };
+
+static void lbm_nccl_destroy(ncclComm_t comm);
 
 namespace {
 
@@ -380,7 +392,170 @@ int use_device(lbm_ctx *c)
 
 }  // namespace
 
+// ---- NCCL, resolved at run time ----
+namespace {
+
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    std::string error;
+};
+
+NcclApi &nccl()
+{
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api;
+    tried = true;
+    // RTLD_NOLOAD first: under torchrun the process already holds torch's libnccl.so.2
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) {
+        api.error = std::string("cannot load libnccl.so.2: ") + dlerror();
+        return api;
+    }
+    api.handle = h;
+#define LBM_NCCL_SYM(field, name)                                             \
+    do {                                                                      \
+        *(void **)(&api.field) = dlsym(h, name);                              \
+        if (!api.field) api.error = std::string("libnccl lacks ") + name;     \
+    } while (0)
+    LBM_NCCL_SYM(GetUniqueId, "ncclGetUniqueId");
+    LBM_NCCL_SYM(CommInitRank, "ncclCommInitRank");
+    LBM_NCCL_SYM(CommDestroy, "ncclCommDestroy");
+    LBM_NCCL_SYM(Send, "ncclSend");
+    LBM_NCCL_SYM(Recv, "ncclRecv");
+    LBM_NCCL_SYM(GroupStart, "ncclGroupStart");
+    LBM_NCCL_SYM(GroupEnd, "ncclGroupEnd");
+    LBM_NCCL_SYM(GetErrorString, "ncclGetErrorString");
+#undef LBM_NCCL_SYM
+    return api;
+}
+
+#define LBM_NCCL(ctx, call)                                                                             \
+    do {                                                                                                \
+        ncclResult_t r__ = (call);                                                                      \
+        if (r__ != ncclSuccess)                                                                         \
+            return fail((ctx), LBM_ERR_CUDA, "%s:%d %s(%d) - %s", __FILE__, __LINE__, #call, (int)r__,  \
+                        nccl().GetErrorString ? nccl().GetErrorString(r__) : "?");                      \
+    } while (0)
+
+// The overlapped z-slab schedule of one rank (see include/lbm_b200.h, transport 2b).
+//   bstream: wait interior(k-1) -> boundary planes(k) -> [advance] pack -> send/recv -> unpack
+//   stream : wait boundary kernels(k-1) -> interior planes(k)
+// The events alternate with the iteration parity; everything is enqueued without host synchronisation.
+int run_slab_with_comm(lbm_ctx *c, int n_iterations, int every)
+{
+    NcclApi &n = nccl();
+    const bool has_lo = c->z_begin > 0, has_hi = c->z_end < c->dim;
+    const ncclDataType_t dt = c->p.precision == LBM_F32 ? ncclFloat32 : ncclFloat64;
+    const size_t count = (size_t)5 * c->dim * c->dim;
+    cudaStream_t S = c->stream, B = c->bstream;
+    // the boundary stream starts after whatever the main stream was asked to do before
+    LBM_CUDA(c, cudaEventRecord(c->ev_join, S));
+    LBM_CUDA(c, cudaStreamWaitEvent(B, c->ev_join, 0));
+    for (int i = 0; i < n_iterations; ++i) {
+        const int64_t it = c->iteration + 1;
+        const bool macro = every != 0 && (it % every) == 0;
+        const int par = (int)(it & 1), prev = par ^ 1;
+        const int zlo = c->z_begin, zhi = c->z_end - 1;
+        LBM_CUDA(c, cudaStreamWaitEvent(B, c->ev_in[prev], 0));
+        if (has_lo) LBM_CUDA(c, launch_step(c, zlo, zlo + 1, macro, B));
+        if (has_hi && !(has_lo && zhi == zlo)) LBM_CUDA(c, launch_step(c, zhi, zhi + 1, macro, B));
+        LBM_CUDA(c, cudaEventRecord(c->ev_bk[par], B));
+
+        LBM_CUDA(c, cudaStreamWaitEvent(S, c->ev_bk[prev], 0));
+        LBM_CUDA(c, launch_step(c, zlo + (has_lo ? 1 : 0), c->z_end - (has_hi ? 1 : 0), macro, S));
+        LBM_CUDA(c, cudaEventRecord(c->ev_in[par], S));
+
+        c->cur ^= 1;
+        c->iteration = it;
+
+        // exchange on the boundary stream (pack / unpack use c->stream: point it at B for a moment)
+        c->stream = B;
+        int rc = lbm_halo_pack(c);
+        if (rc == LBM_OK) {
+            ncclResult_t r = n.GroupStart();
+            if (r == ncclSuccess && has_hi) r = n.Send(c->halo_send[1], count, dt, c->comm_rank + 1, c->comm, B);
+            if (r == ncclSuccess && has_hi) r = n.Recv(c->halo_recv[1], count, dt, c->comm_rank + 1, c->comm, B);
+            if (r == ncclSuccess && has_lo) r = n.Send(c->halo_send[0], count, dt, c->comm_rank - 1, c->comm, B);
+            if (r == ncclSuccess && has_lo) r = n.Recv(c->halo_recv[0], count, dt, c->comm_rank - 1, c->comm, B);
+            const ncclResult_t e = n.GroupEnd();
+            if (r == ncclSuccess) r = e;
+            if (r != ncclSuccess) {
+                c->stream = S;
+                return fail(c, LBM_ERR_CUDA, "NCCL halo exchange failed (%d) - %s", (int)r, n.GetErrorString(r));
+            }
+            rc = lbm_halo_unpack(c);
+        }
+        c->stream = S;
+        if (rc != LBM_OK) return rc;
+    }
+    // the main stream's timeline ends after the last exchange
+    LBM_CUDA(c, cudaEventRecord(c->ev_join, B));
+    LBM_CUDA(c, cudaStreamWaitEvent(S, c->ev_join, 0));
+    return LBM_OK;
+}
+
+}  // namespace
+
+static void lbm_nccl_destroy(ncclComm_t comm)
+{
+    if (comm && nccl().CommDestroy) nccl().CommDestroy(comm);
+}
+
 extern "C" {
+
+int lbm_comm_unique_id(uint8_t id[LBM_COMM_ID_BYTES])
+{
+    static_assert(sizeof(ncclUniqueId) == LBM_COMM_ID_BYTES, "ncclUniqueId size");
+    if (!id) return LBM_ERR_INVALID;
+    NcclApi &n = nccl();
+    if (!n.error.empty() || !n.GetUniqueId) return fail(nullptr, LBM_ERR_CUDA, "lbm_comm_unique_id: %s", n.error.c_str());
+    ncclUniqueId u;
+    const ncclResult_t r = n.GetUniqueId(&u);
+    if (r != ncclSuccess) return fail(nullptr, LBM_ERR_CUDA, "ncclGetUniqueId(%d) - %s", (int)r, n.GetErrorString(r));
+    std::memcpy(id, &u, sizeof u);
+    return LBM_OK;
+}
+
+int lbm_comm_init(lbm_ctx *c, const uint8_t id[LBM_COMM_ID_BYTES], int rank, int world)
+{
+    if (!c || !id) return LBM_ERR_INVALID;
+    if (c->comm) return fail(c, LBM_ERR_STATE, "lbm_comm_init: already initialised");
+    if (c->aa) return fail(c, LBM_ERR_INVALID, "lbm_comm_init: the AA variant is single-device");
+    if (world < 1 || rank < 0 || rank >= world) return fail(c, LBM_ERR_INVALID, "lbm_comm_init: rank %d of %d", rank, world);
+    // the slabs must tile the cube in rank order
+    if ((rank == 0) != (c->z_begin == 0) || (rank == world - 1) != (c->z_end == c->dim))
+        return fail(c, LBM_ERR_INVALID, "lbm_comm_init: planes [%d, %d) do not fit rank %d of %d", c->z_begin,
+                    c->z_end, rank, world);
+    NcclApi &n = nccl();
+    if (!n.error.empty()) return fail(c, LBM_ERR_CUDA, "lbm_comm_init: %s", n.error.c_str());
+    int rc = use_device(c);
+    if (rc != LBM_OK) return rc;
+    int lo = 0, hi = 0;
+    LBM_CUDA(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    LBM_CUDA(c, cudaStreamCreateWithPriority(&c->bstream, cudaStreamNonBlocking, hi));
+    for (int i = 0; i < 2; ++i) {
+        LBM_CUDA(c, cudaEventCreateWithFlags(&c->ev_bk[i], cudaEventDisableTiming));
+        LBM_CUDA(c, cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
+    }
+    LBM_CUDA(c, cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    ncclUniqueId u;
+    std::memcpy(&u, id, sizeof u);
+    LBM_NCCL(c, n.CommInitRank(&c->comm, world, u, rank));
+    c->comm_rank = rank;
+    c->comm_world = world;
+    return LBM_OK;
+}
 
 void lbm_default_params(lbm_params *p)
 {
@@ -413,6 +588,14 @@ void lbm_destroy(lbm_ctx *c)
         if (e.start) cudaEventDestroy(e.start);
         if (e.stop) cudaEventDestroy(e.stop);
     }
+    if (c->bstream) cudaStreamSynchronize(c->bstream);
+    if (c->comm) lbm_nccl_destroy(c->comm);
+    for (int i = 0; i < 2; ++i) {
+        if (c->ev_bk[i]) cudaEventDestroy(c->ev_bk[i]);
+        if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
+    }
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->bstream) cudaStreamDestroy(c->bstream);
     if (c->ev_init_start) cudaEventDestroy(c->ev_init_start);
     if (c->ev_last) cudaEventDestroy(c->ev_last);
     for (int i = 0; i < 2; ++i) {
@@ -650,12 +833,16 @@ int lbm_run(lbm_ctx *c, int n_iterations, int every)
     if ((rc = push_pair(c, &ep)) != LBM_OK) return rc;
     c->compute_events.push_back(ep);
     LBM_CUDA(c, cudaEventRecord(ep.start, c->stream));
-    for (int i = 0; i < n_iterations; ++i) {
-        const int64_t it = c->iteration + 1;  // 1-based like lbmcl.hpp:435
-        const bool macro = every != 0 && (it % every) == 0;
-        LBM_CUDA(c, launch_step(c, c->z_begin, c->z_end, macro, c->stream));
-        c->cur ^= 1;
-        c->iteration = it;
+    if (c->comm) {
+        if ((rc = run_slab_with_comm(c, n_iterations, every)) != LBM_OK) return rc;
+    } else {
+        for (int i = 0; i < n_iterations; ++i) {
+            const int64_t it = c->iteration + 1;  // 1-based like lbmcl.hpp:435
+            const bool macro = every != 0 && (it % every) == 0;
+            LBM_CUDA(c, launch_step(c, c->z_begin, c->z_end, macro, c->stream));
+            c->cur ^= 1;
+            c->iteration = it;
+        }
     }
     LBM_CUDA(c, cudaEventRecord(ep.stop, c->stream));
     return record_last(c);
@@ -857,6 +1044,7 @@ static cudaError_t halo_launch(lbm_ctx *c, void *lattice, void *dense, long long
     const int bx = c->dim < 256 ? c->dim : 256;
     const dim3 b(bx, 1, 1), g(c->dim / bx, c->dim, 5);
     halo_kernel<T, PACK><<<g, b, 0, c->stream>>>((T *)lattice, (T *)dense, c->dim, plane_local, c->lay, dir_up);
+    c->launches += 1;
     return cudaGetLastError();
 }
 

@@ -26,7 +26,10 @@ def main():
     dev = torch.device("cuda", lr)
     dist.init_process_group("nccl", device_id=dev)
     ok = True
-    for precision, dim, stride, its in (("f32", 32, 32, 10), ("f64", 64, 32, 6)):
+    for transport, precision, dim, stride, its in (("host", "f32", 32, 32, 10), ("host", "f64", 64, 32, 6),
+                                                   ("nccl-in-library", "f32", 32, 32, 10),
+                                                   ("nccl-in-library", "f64", 64, 32, 7),
+                                                   ("nccl-in-library", "f32", 128, 32, 20)):
         z0, z1 = slab_range(dim, world, rank)
         sim = Simulation(dim=dim, precision=precision, stride=stride, device=lr, z_range=(z0, z1))
         main_s = torch.cuda.Stream(device=dev)
@@ -39,14 +42,25 @@ def main():
         recv = [torch.as_tensor(DevBuf(sim.halo_recv_ptr(f), n_h, ts), device=dev) if ok_ else None
                 for f, ok_ in ((0, has_lo), (1, has_hi))]
         sim.init()
-        with torch.cuda.stream(main_s):
-            for it in range(1, its + 1):
-                sim.step_planes(z0, z1, it == its)
-                sim.advance()
-                sim.halo_pack()
-                for r in exchange_halos(send, recv, world, rank):
-                    r.wait()
-                sim.halo_unpack()
+        if transport == "host":
+            # split-phase ABI, exchange posted by the host through torch.distributed
+            with torch.cuda.stream(main_s):
+                for it in range(1, its + 1):
+                    sim.step_planes(z0, z1, it == its)
+                    sim.advance()
+                    sim.halo_pack()
+                    for r in exchange_halos(send, recv, world, rank):
+                        r.wait()
+                    sim.halo_unpack()
+        else:
+            # library-driven: NCCL communicator inside the context, overlapped schedule in lbm_run
+            uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+            if rank == 0:
+                uid.copy_(torch.frombuffer(bytearray(Simulation.comm_unique_id()), dtype=torch.uint8))
+            dist.broadcast(uid, 0)
+            sim.comm_init(uid.cpu().numpy().tobytes(), rank, world)
+            sim.run(its - 3, its)
+            sim.run(3, its)
         n = dim ** 3
         npd = np.float32 if precision == "f32" else np.float64
         rho = np.full(n, np.nan, dtype=npd)
@@ -70,7 +84,7 @@ def main():
                 full_rho[sl] = a[:n][sl]
                 full_u[:, sl] = a[n:].reshape(3, n)[:, sl]
             same = full_rho.tobytes() == exp["rho"][1].tobytes() and full_u.tobytes() == exp["u"][1].tobytes()
-            print(f"multi_gpu_check {precision} {dim}^3 x{its} on {world} ranks: {'bit-identical' if same else 'MISMATCH'}")
+            print(f"multi_gpu_check [{transport}] {precision} {dim}^3 x{its} on {world} ranks: {'bit-identical' if same else 'MISMATCH'}")
             ok = ok and same
     dist.barrier()
     dist.destroy_process_group()
