@@ -87,6 +87,11 @@ struct lbm_ctx {
     int64_t launches = 0;
     bool initialised = false;
 
+    // CUDA graphs of LBM_GRAPH_CHUNK unflagged iterations for launch-bound (small) lattices,
+    // one per starting parity
+    cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
+    cudaStream_t graph_stream = nullptr;  // the stream the graphs were captured on
+
     // profiling (the reference's event list, lbmcl.hpp:74)
     cudaEvent_t ev_init_start = nullptr;
     cudaEvent_t ev_last = nullptr;
@@ -392,6 +397,56 @@ int use_device(lbm_ctx *c)
 
 }  // namespace
 
+// ---- CUDA graphs for launch-bound lattices ----
+namespace {
+
+constexpr int LBM_GRAPH_CHUNK = 16;     // even: lattice parity and AA step type are restored after a chunk
+constexpr int LBM_GRAPH_MAX_DIM = 64;   // above this one launch takes longer than its enqueue
+
+// Enqueue LBM_GRAPH_CHUNK iterations without macro store as ONE graph launch.  The graph is captured
+// on first use for the current parity (source lattice / AA step type) and stream, then replayed.
+int launch_graph_chunk(lbm_ctx *c)
+{
+    const int par = c->aa ? (int)(c->iteration & 1) : c->cur;
+    if (c->graph_stream != c->stream) {  // captured on another stream: rebuild
+        for (int i = 0; i < 2; ++i)
+            if (c->graph_exec[i]) {
+                cudaGraphExecDestroy(c->graph_exec[i]);
+                c->graph_exec[i] = nullptr;
+            }
+        c->graph_stream = c->stream;
+    }
+    const int cur0 = c->cur;
+    const int64_t it0 = c->iteration, launches0 = c->launches;
+    if (!c->graph_exec[par]) {
+        cudaGraph_t graph = nullptr;
+        LBM_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        cudaError_t e = cudaSuccess;
+        for (int i = 0; i < LBM_GRAPH_CHUNK && e == cudaSuccess; ++i) {
+            e = launch_step(c, c->z_begin, c->z_end, false, c->stream);
+            c->cur ^= 1;
+            c->iteration += 1;
+        }
+        const cudaError_t e2 = cudaStreamEndCapture(c->stream, &graph);
+        c->cur = cur0;
+        c->iteration = it0;
+        c->launches = launches0;
+        if (e != cudaSuccess || e2 != cudaSuccess) {
+            if (graph) cudaGraphDestroy(graph);
+            LBM_CUDA(c, e != cudaSuccess ? e : e2);
+        }
+        const cudaError_t e3 = cudaGraphInstantiate(&c->graph_exec[par], graph, 0);
+        cudaGraphDestroy(graph);
+        LBM_CUDA(c, e3);
+    }
+    LBM_CUDA(c, cudaGraphLaunch(c->graph_exec[par], c->stream));
+    c->iteration += LBM_GRAPH_CHUNK;  // even chunk: c->cur unchanged
+    c->launches += LBM_GRAPH_CHUNK;
+    return LBM_OK;
+}
+
+}  // namespace
+
 // ---- NCCL, resolved at run time ----
 namespace {
 
@@ -588,6 +643,8 @@ void lbm_destroy(lbm_ctx *c)
         if (e.start) cudaEventDestroy(e.start);
         if (e.stop) cudaEventDestroy(e.stop);
     }
+    for (int i = 0; i < 2; ++i)
+        if (c->graph_exec[i]) cudaGraphExecDestroy(c->graph_exec[i]);
     if (c->bstream) cudaStreamSynchronize(c->bstream);
     if (c->comm) lbm_nccl_destroy(c->comm);
     for (int i = 0; i < 2; ++i) {
@@ -836,12 +893,25 @@ int lbm_run(lbm_ctx *c, int n_iterations, int every)
     if (c->comm) {
         if ((rc = run_slab_with_comm(c, n_iterations, every)) != LBM_OK) return rc;
     } else {
-        for (int i = 0; i < n_iterations; ++i) {
+        int left = n_iterations;
+        while (left > 0) {
             const int64_t it = c->iteration + 1;  // 1-based like lbmcl.hpp:435
+            // launch-bound lattices: replay a captured chunk of unflagged iterations as one graph
+            if (c->dim <= LBM_GRAPH_MAX_DIM && left >= LBM_GRAPH_CHUNK && c->peer[0] == nullptr &&
+                c->peer[1] == nullptr) {
+                const int64_t last = it + LBM_GRAPH_CHUNK - 1;
+                const bool flagged = every != 0 && (last / every) != ((it - 1) / every);
+                if (!flagged) {
+                    if ((rc = launch_graph_chunk(c)) != LBM_OK) return rc;
+                    left -= LBM_GRAPH_CHUNK;
+                    continue;
+                }
+            }
             const bool macro = every != 0 && (it % every) == 0;
             LBM_CUDA(c, launch_step(c, c->z_begin, c->z_end, macro, c->stream));
             c->cur ^= 1;
             c->iteration = it;
+            --left;
         }
     }
     LBM_CUDA(c, cudaEventRecord(ep.stop, c->stream));

@@ -171,12 +171,27 @@ __device__ __forceinline__ void collide_fluid(T (&f)[Q], const Consts<T> &c, T &
     const T u2 = A::add(A::add(A::mul(ux, ux), A::mul(uy, uy)), A::mul(uz, uz));
     const T c15u2 = A::mul(T(1.5), u2);
     const T rw[3] = { A::mul(rho, c.w[0]), A::mul(rho, c.w[1]), A::mul(rho, c.w[2]) };
-    // kernels.cl:412-418 with compute_bgk (kernels.cl:270-273): f + INV_TAU * (feq - f)
+    // kernels.cl:412-418 with compute_bgk (kernels.cl:270-273): f + INV_TAU * (feq - f).
+    // Opposite directions are evaluated together: e_o.u == -(e_q.u) exactly, hence 3*eu changes sign
+    // exactly, (4.5*eu)*eu is identical, and 1 + (-(3eu)) == 1 - 3eu bit for bit -- the reference's
+    // individually rounded operations, nine of them shared instead of repeated.
     static_for<Q>([&](auto qc) {
         constexpr int q = decltype(qc)::value;
-        const T eu = e_dot_u<A, q>(ux, uy, uz);
-        const T feq = A::mul(rw[wclass(q)], eq_poly<A>(eu, c15u2));
-        f[q] = A::add(f[q], A::mul(c.inv_tau, A::sub(feq, f[q])));
+        constexpr int o = opp(q);
+        if constexpr (q == 0) {
+            const T feq = A::mul(rw[0], eq_poly<A>(T(0), c15u2));
+            f[0] = A::add(f[0], A::mul(c.inv_tau, A::sub(feq, f[0])));
+        } else if constexpr (q < o) {
+            const T eu = e_dot_u<A, q>(ux, uy, uz);
+            const T a3 = A::mul(T(3), eu);
+            const T sq = A::mul(A::mul(T(4.5), eu), eu);
+            const T pq = A::sub(A::add(A::add(T(1), a3), sq), c15u2);
+            const T po = A::sub(A::add(A::sub(T(1), a3), sq), c15u2);
+            const T fq = A::mul(rw[wclass(q)], pq);
+            const T fo = A::mul(rw[wclass(o)], po);
+            f[q] = A::add(f[q], A::mul(c.inv_tau, A::sub(fq, f[q])));
+            f[o] = A::add(f[o], A::mul(c.inv_tau, A::sub(fo, f[o])));
+        }
     });
 }
 

@@ -1,0 +1,73 @@
+#!/bin/bash
+# Parameter sweep of the host program, the B200 counterpart of the reference's benchmark.sh:
+# same protocol (reference benchmark.sh:8-15, 60-107: -i 50 -e 0, REPS repetitions per configuration,
+# the ';'-separated statistics line of stderr appended to benchmarks/stats.csv) and the same
+# aggregation (benchmark.sh:109-176: per configuration drop the fastest and the slowest run by total
+# time and average the rest) into benchmarks/benchmark.csv.
+# The work-group size is not swept: on this path it is a hint that does not change the CUDA block.
+#
+#   ./benchmark.sh                      # fp32, dims 8..256
+#   PRECISION=double DIMS="64 128 256 512" GPUS=1 ./benchmark.sh
+set -e
+cd "$(dirname "$0")"
+
+BENCHMARK_DIR=./benchmarks
+LOG=$BENCHMARK_DIR/stats.csv
+OUT=$BENCHMARK_DIR/benchmark.csv
+PRECISION=${PRECISION:-single}
+DEVICE=${DEVICE:-0}
+GPUS=${GPUS:-1}
+VISCOSITY=0.0089
+VELOCITY=0.05
+ITERATIONS=${ITERATIONS:-50}
+EVERY=0
+REPS=${REPS:-10}
+DIMS=${DIMS:-"8 16 32 64 128 256"}
+STRIDES=${STRIDES:-"1 8 16 32 64 128 full"}
+OPTIMIZE=${OPTIMIZE:-"-o"}          # the reference sweep runs with -o; set OPTIMIZE="" for strict kernels
+EXTRA=${EXTRA:-}                    # e.g. EXTRA=-A for the in-place AA kernels
+
+mkdir -p $BENCHMARK_DIR
+rm -f $LOG $OUT
+make -s lbmcl
+
+FLAGS="$OPTIMIZE $EXTRA"
+[ "$PRECISION" = double ] && FLAGS="$FLAGS -F"
+[ "$GPUS" != 1 ] && FLAGS="$FLAGS -G $GPUS"
+
+for d in $DIMS; do
+    for s in $STRIDES; do
+        [ "$s" = full ] && s=$((d * d * d))
+        [ "$s" -gt $((d * d * d)) ] && continue
+        for r in $(seq 1 "$REPS"); do
+            ./lbmcl -D "$DEVICE" -d "$d" -n $VISCOSITY -u $VELOCITY -i "$ITERATIONS" -e $EVERY -s "$s" $FLAGS \
+                2>> $LOG > /dev/null
+        done
+    done
+done
+
+# device;precision;dim;iterations;every;lws;stride;optimize;total_ms;kernels_ms;MLUPS;kernelsMLUPS
+awk -F';' '
+{
+    key = $1 FS $2 FS $3 FS $4 FS $5 FS $6 FS $7 FS $8
+    n[key]++
+    i = n[key]
+    tot[key, i] = $9; ker[key, i] = $10; ml[key, i] = $11; kml[key, i] = $12
+    if (!(key in order)) { order[key] = ++nkeys; keys[nkeys] = key }
+}
+END {
+    print "device;precision;dim;iterations;every;lws;stride;optimize;runs;total_ms;kernels_ms;MLUPS;kernelsMLUPS"
+    for (k = 1; k <= nkeys; k++) {
+        key = keys[k]; c = n[key]
+        lo = 1; hi = 1
+        for (i = 2; i <= c; i++) { if (tot[key, i] < tot[key, lo]) lo = i; if (tot[key, i] > tot[key, hi]) hi = i }
+        st = sk = sm = skm = 0; used = 0
+        for (i = 1; i <= c; i++) {
+            if (c > 2 && (i == lo || i == hi)) continue
+            st += tot[key, i]; sk += ker[key, i]; sm += ml[key, i]; skm += kml[key, i]; used++
+        }
+        printf "%s;%d;%.6g;%.6g;%.6g;%.6g\n", key, used, st / used, sk / used, sm / used, skm / used
+    }
+}' $LOG > $OUT
+echo "wrote $LOG and $OUT"
+column -s';' -t $OUT | cut -c1-200

@@ -285,3 +285,27 @@ def test_aa_variant_uses_half_the_lattice_memory_and_matches_at_size():
     from lbmcl_b200.capi import LbmError
     with pytest.raises(LbmError):
         _sim(dim=32, variant=8, z_range=(0, 16))
+
+
+@pytest.mark.parametrize("variant", [1, 8])
+@pytest.mark.parametrize("every", [0, 7, 16, 33])
+def test_graph_chunks_from_any_parity(every, variant):
+    """Small lattices replay 16-iteration CUDA graphs inside lbm_run; chunks must start correctly from
+    either lattice parity and step around the iterations that store rho/u."""
+    dim, stride, nu, u_lid = 16, 16, 0.0089, 0.05
+    o = Oracle("f32")
+    st = o.alloc(dim)
+    o.init(st, dim, stride, nu, u_lid)
+    with _sim(dim=dim, stride=stride, variant=variant) as s:
+        s.init()
+        done = 0
+        for n in (5, 40, 1, 35, 16):
+            s.run(n, every)
+            for it in range(done + 1, done + n + 1):
+                o.step(st, dim, stride, nu, u_lid, it, every)
+            done += n
+            rho, u = s.read_macros()
+            assert rho.tobytes() == st["rho"].tobytes() and u.tobytes() == st["u"].reshape(3, -1).tobytes(), (done, every)
+            exp_f = st["f_stream"] if (done + 1) % 2 == 0 else st["f_collide"]
+            assert s.read_f().tobytes() == exp_f.tobytes(), done
+        assert s.iteration == done and s.launch_count == done
