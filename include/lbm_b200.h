@@ -118,6 +118,10 @@ int lbm_sync(lbm_ctx *ctx);
  * writes only its owned planes.  Either pointer may be NULL.  Element type = the context's precision. */
 int lbm_read_macros(lbm_ctx *ctx, void *rho_host, void *u_host);
 
+/* The same for a slab context without a cube-sized host array: rho -> host[P], u -> host[3][P] with
+ * P = (z_end - z_begin) * DIM^2, i.e. only the owned planes, compact. */
+int lbm_read_macros_slab(lbm_ctx *ctx, void *rho_slab, void *u_slab);
+
 /* Blocking readback of the cell-type map (lbmcl.hpp:164 inside storeMap), global layout int32[N]. */
 int lbm_read_map(lbm_ctx *ctx, int32_t *map_host);
 

@@ -21,7 +21,7 @@ VARIANT_AUTO, VARIANT_SCALAR, VARIANT_VEC2, VARIANT_VEC4, VARIANT_AA = 0, 1, 2, 
 # every symbol include/lbm_b200.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "lbm_default_params", "lbm_create", "lbm_destroy", "lbm_last_error", "lbm_init", "lbm_step", "lbm_run",
-    "lbm_sync", "lbm_read_macros", "lbm_read_map", "lbm_read_f", "lbm_time_ms", "lbm_device_name",
+    "lbm_sync", "lbm_read_macros", "lbm_read_macros_slab", "lbm_read_map", "lbm_read_f", "lbm_time_ms", "lbm_device_name",
     "lbm_effective_params", "lbm_block_shape", "lbm_device_bytes", "lbm_launch_count", "lbm_iteration",
     "lbm_set_stream", "lbm_step_planes", "lbm_advance", "lbm_z_range", "lbm_halo_elems", "lbm_halo_send_buffer", "lbm_halo_recv_buffer", "lbm_halo_pack",
     "lbm_halo_unpack", "lbm_comm_unique_id", "lbm_comm_init", "lbm_group_create", "lbm_group_destroy", "lbm_group_last_error", "lbm_group_size",
@@ -82,6 +82,7 @@ def load() -> ctypes.CDLL:
     lib.lbm_run.argtypes = [vp, ci, ci]
     lib.lbm_sync.argtypes = [vp]
     lib.lbm_read_macros.argtypes = [vp, vp, vp]
+    lib.lbm_read_macros_slab.argtypes = [vp, vp, vp]
     lib.lbm_read_map.argtypes = [vp, vp]
     lib.lbm_read_f.argtypes = [vp, vp]
     lib.lbm_time_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
@@ -214,6 +215,17 @@ class Simulation:
         if u is None:
             u = np.full((3, n), np.nan, dtype=self.dtype)
         self._check(self.lib.lbm_read_macros(self.h, _ptr(rho), _ptr(u)))
+        return rho, u
+
+    def read_macros_slab(self, rho=None, u=None):
+        """rho[P], u[3, P] over the owned planes only (P = planes * dim^2)."""
+        z0, z1 = self.z_range
+        p = (z1 - z0) * self.dim * self.dim
+        if rho is None:
+            rho = np.full(p, np.nan, dtype=self.dtype)
+        if u is None:
+            u = np.full((3, p), np.nan, dtype=self.dtype)
+        self._check(self.lib.lbm_read_macros_slab(self.h, _ptr(rho), _ptr(u)))
         return rho, u
 
     def read_map(self):

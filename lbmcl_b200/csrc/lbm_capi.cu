@@ -951,6 +951,27 @@ int lbm_read_macros(lbm_ctx *c, void *rho_host, void *u_host)
     return LBM_OK;
 }
 
+int lbm_read_macros_slab(lbm_ctx *c, void *rho_slab, void *u_slab)
+{
+    if (!c) return LBM_ERR_INVALID;
+    if (!c->initialised) return fail(c, LBM_ERR_STATE, "lbm_read_macros_slab before lbm_init");
+    int rc = use_device(c);
+    if (rc != LBM_OK) return rc;
+    const long long plane = (long long)c->dim * c->dim;
+    const size_t off_local = (size_t)(c->z_begin - c->zs0) * plane * c->esize;
+    const size_t bytes = (size_t)(c->z_end - c->z_begin) * plane * c->esize;
+    if (rho_slab)
+        LBM_CUDA(c, cudaMemcpyAsync(rho_slab, (const char *)c->rho + off_local, bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (u_slab)
+        for (int k = 0; k < 3; ++k)
+            LBM_CUDA(c, cudaMemcpyAsync((char *)u_slab + (size_t)k * bytes,
+                                        (const char *)c->u + (size_t)k * c->n_local * c->esize + off_local, bytes,
+                                        cudaMemcpyDeviceToHost, c->stream));
+    if ((rc = record_last(c)) != LBM_OK) return rc;
+    LBM_CUDA(c, cudaStreamSynchronize(c->stream));
+    return LBM_OK;
+}
+
 int lbm_read_map(lbm_ctx *c, int32_t *map_host)
 {
     if (!c || !map_host) return LBM_ERR_INVALID;

@@ -70,4 +70,4 @@ END {
     }
 }' $LOG > $OUT
 echo "wrote $LOG and $OUT"
-column -s';' -t $OUT | cut -c1-200
+if command -v column > /dev/null; then column -s';' -t $OUT | cut -c1-200; else cat $OUT; fi

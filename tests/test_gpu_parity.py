@@ -250,6 +250,9 @@ def test_dense_halo_transport_matches_single():
     u = np.full((3, n), np.nan)
     lo.read_macros(rho, u)
     hi.read_macros(rho, u)
+    # compact slab read-back = the owned planes of the global arrays
+    r_hi, u_hi = hi.read_macros_slab()
+    assert r_hi.tobytes() == rho[n // 2:].tobytes() and u_hi.tobytes() == np.ascontiguousarray(u[:, n // 2:]).tobytes()
     lo.close()
     hi.close()
     assert rho.tobytes() == exp["rho"][1].tobytes() and u.tobytes() == exp["u"][1].tobytes()
