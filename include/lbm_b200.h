@@ -50,8 +50,12 @@ typedef enum lbm_variant {
     LBM_VARIANT_SCALAR = 1, /* two-lattice pull, one cell per thread                             */
     LBM_VARIANT_VEC2 = 2,   /* two-lattice pull, 2 cells per thread, x shifts by warp shuffle    */
     LBM_VARIANT_VEC4 = 4,   /* two-lattice pull, 4 cells per thread (128-bit fp32 access)        */
-    LBM_VARIANT_AA = 8      /* in-place AA pattern: ONE lattice (half the memory), one cell per
+    LBM_VARIANT_AA = 8,     /* in-place AA pattern: ONE lattice (half the memory), one cell per
                                thread; whole cube on one device only                             */
+    LBM_VARIANT_TMA = 16    /* two-lattice pull fed by the TMA unit: persistent CTAs, bulk-tensor
+                               loads into an mbarrier ring of row tiles, bulk-tensor stores back;
+                               needs stride <= DIM, stride*sizeof(T) >= 16, DIM >= 32 (else the
+                               scalar variant is used)                                           */
 } lbm_variant;
 
 /*

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(HERE, "csrc", "liblbm_b200.so")
 
 ABI_VERSION = 1
 F32, F64 = 0, 1
-VARIANT_AUTO, VARIANT_SCALAR, VARIANT_VEC2, VARIANT_VEC4, VARIANT_AA = 0, 1, 2, 4, 8
+VARIANT_AUTO, VARIANT_SCALAR, VARIANT_VEC2, VARIANT_VEC4, VARIANT_AA, VARIANT_TMA = 0, 1, 2, 4, 8, 16
 
 # every symbol include/lbm_b200.h declares (tests check that the library exports all of them)
 EXPORTS = [

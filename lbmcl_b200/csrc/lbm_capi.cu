@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "lbm_kernels.cuh"
+#include "lbm_tma.cuh"
 
 using namespace lbm;
 
@@ -49,6 +50,11 @@ struct lbm_ctx {
     Layout lay{};
     int layout_mode = LM_GENERIC;
     bool aa = false;             // in-place AA variant: only f[0] exists
+    bool tma = false;            // TMA-fed variant: tensor maps of the two lattices
+    CUtensorMap tmap[2];
+    int tma_tx = 0, tma_ns = 0, tma_grid = 0;
+    size_t tma_smem = 0;
+    int *tma_error = nullptr;    // device flag set by a kernel whose mbarrier wait timed out
     int vec = 1;
     dim3 block{1, 1, 1};
     size_t esize = 4;
@@ -100,6 +106,7 @@ struct lbm_ctx {
 };
 
 static void lbm_nccl_destroy(ncclComm_t comm);
+static int setup_tma(lbm_ctx *c, int n_sm);
 
 namespace {
 
@@ -287,12 +294,71 @@ cudaError_t launch_aa_t(lbm_ctx *c, const StepArgs<T> &a, bool macro, cudaStream
     return cudaGetLastError();
 }
 
+// TMA-fed variant: persistent CTAs over the live rows of [z_begin, z_end).
+template <typename T, int TX>
+cudaError_t launch_tma_tx(lbm_ctx *c, const StepArgs<T> &sa, const TmaArgs<T> &a, bool macro, cudaStream_t s, int grid)
+{
+    const bool fast = c->p.fast_math != 0;
+    const CUtensorMap &ms = c->tmap[c->cur], &md = c->tmap[c->cur ^ 1];
+    (void)sa;
+#define LBM_TMA_LAUNCH(F, M)                                                                                    \
+    do {                                                                                                        \
+        static bool attr_done = false;                                                                          \
+        if (!attr_done) {                                                                                       \
+            cudaError_t e = cudaFuncSetAttribute(step_tma_kernel<T, F, M, TX>,                                  \
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);     \
+            if (e != cudaSuccess) return e;                                                                     \
+            attr_done = true;                                                                                   \
+        }                                                                                                       \
+        step_tma_kernel<T, F, M, TX><<<grid, TX, c->tma_smem, s>>>(ms, md, a, c->tma_error);                   \
+    } while (0)
+    if (fast) { if (macro) LBM_TMA_LAUNCH(true, true); else LBM_TMA_LAUNCH(true, false); }
+    else      { if (macro) LBM_TMA_LAUNCH(false, true); else LBM_TMA_LAUNCH(false, false); }
+#undef LBM_TMA_LAUNCH
+    c->launches += 1;
+    return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_tma_t(lbm_ctx *c, const StepArgs<T> &sa, bool macro, cudaStream_t s)
+{
+    // live planes of this launch
+    const int zf = sa.z_begin < 1 ? 1 : sa.z_begin;
+    const int zl = sa.z_end > c->dim - 1 ? c->dim - 1 : sa.z_end;
+    if (zl <= zf) return cudaSuccess;
+    TmaArgs<T> a{};
+    a.src = sa.src;
+    a.rho = sa.rho;
+    a.u = sa.u;
+    a.dim = c->dim;
+    a.zs0 = c->zs0;
+    a.z_first = zf;
+    a.n_xseg = c->dim / c->tma_tx;
+    a.n_tiles = (zl - zf) * (c->dim - 2) * a.n_xseg;
+    a.ns = c->tma_ns;
+    a.n_local = c->n_local;
+    a.lay = c->lay;
+    a.c = sa.c;
+    for (int i = 0; i < 2; ++i)
+        for (int q = 0; q < Q; ++q) a.stale[i][q] = sa.stale[i][q];
+    const int grid = a.n_tiles < c->tma_grid ? a.n_tiles : c->tma_grid;
+    switch (c->tma_tx) {
+        case 256: return launch_tma_tx<T, 256>(c, sa, a, macro, s, grid);
+        case 128: return launch_tma_tx<T, 128>(c, sa, a, macro, s, grid);
+        case 64: return launch_tma_tx<T, 64>(c, sa, a, macro, s, grid);
+        default: return launch_tma_tx<T, 32>(c, sa, a, macro, s, grid);
+    }
+}
+
 template <typename T>
 cudaError_t launch_step_p(lbm_ctx *c, int z_begin, int z_end, bool macro, cudaStream_t s,
                           const Consts<T> &k, const T (&stale)[2][Q])
 {
     const StepArgs<T> a = make_step_args<T>(c, z_begin, z_end, k, stale);
     if (c->aa) return launch_aa_t<T>(c, a, macro, s);
+    const bool peer0 = (a.peer_lo != nullptr && z_begin <= c->z_begin && c->z_begin < z_end) ||
+                       (a.peer_hi != nullptr && z_begin <= c->z_end - 1 && c->z_end - 1 < z_end);
+    if (c->tma && !peer0) return launch_tma_t<T>(c, a, macro, s);
     const bool peer = (a.peer_lo != nullptr && z_begin <= c->z_begin && c->z_begin < z_end) ||
                       (a.peer_hi != nullptr && z_begin <= c->z_end - 1 && c->z_end - 1 < z_end);
     switch (c->vec) {
@@ -562,6 +628,58 @@ int run_slab_with_comm(lbm_ctx *c, int n_iterations, int every)
 
 }  // namespace
 
+// Tensor maps of the two lattices for the TMA-fed variant: the CSoA lattice as the 3-D tensor
+// [block][q][stride]; box = one x-row segment of one direction.
+static int setup_tma(lbm_ctx *c, int n_sm)
+{
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                 const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    LBM_CUDA(c, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess)
+        return fail(c, LBM_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+    EncodeFn encode = reinterpret_cast<EncodeFn>(fn);
+
+    const long long S = c->lay.qpitch();
+    c->tma_tx = c->dim < 256 ? c->dim : 256;
+    if (const char *e = std::getenv("LBM_TMA_TX")) {  // test hook: narrower tiles => several segments per row
+        const int v = std::atoi(e);
+        if ((v == 32 || v == 64 || v == 128 || v == 256) && v <= c->dim) c->tma_tx = v;
+    }
+    const cuuint64_t gdim[3] = {(cuuint64_t)S, (cuuint64_t)Q, (cuuint64_t)(c->n_alloc / S)};
+    const cuuint64_t gstride[2] = {(cuuint64_t)(S * c->esize), (cuuint64_t)(Q * S * c->esize)};
+    const cuuint32_t b0 = (cuuint32_t)(S < c->tma_tx ? S : c->tma_tx);
+    const cuuint32_t box[3] = {b0, 1u, (cuuint32_t)(c->tma_tx / b0)};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    const CUtensorMapDataType dt = c->p.precision == LBM_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64;
+    for (int i = 0; i < 2; ++i) {
+        const CUresult r = encode(&c->tmap[i], dt, 3, c->f[i], gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(c, LBM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    }
+    // ring depth / resident CTAs (profiles/r01_tma_experiment.md): the kernel is latency-bound per CTA,
+    // so the shallowest ring with the most resident CTAs wins: 2 stages, as many CTAs as fit in 200 KB
+    const size_t stage = (size_t)Q * c->tma_tx * c->esize;
+    int ns = 2;
+    int ctas = (int)((200 * 1024) / (2 * stage + 1024));
+    if (ctas > 5) ctas = 5;
+    if (const char *e = std::getenv("LBM_TMA_NS")) ns = std::atoi(e);
+    if (const char *e = std::getenv("LBM_TMA_CTAS")) ctas = std::atoi(e);
+    if (ns < 2) ns = 2;
+    if (ctas < 1) ctas = 1;
+    while (ns > 2 && (size_t)ns * stage + 64 > 200 * 1024) --ns;
+    c->tma_ns = ns;
+    c->tma_smem = (size_t)ns * stage + (size_t)ns * sizeof(uint64_t);
+    if (c->tma_smem > 200 * 1024) return fail(c, LBM_ERR_INVALID, "TMA variant: tile ring does not fit shared memory");
+    c->tma_grid = ctas * n_sm;
+    LBM_CUDA(c, cudaMalloc(&c->tma_error, sizeof(int)));
+    LBM_CUDA(c, cudaMemset(c->tma_error, 0, sizeof(int)));
+    return LBM_OK;
+}
+
 static void lbm_nccl_destroy(ncclComm_t comm)
 {
     if (comm && nccl().CommDestroy) nccl().CommDestroy(comm);
@@ -662,6 +780,7 @@ void lbm_destroy(lbm_ctx *c)
     }
     if (c->rho) cudaFree(c->rho);
     if (c->u) cudaFree(c->u);
+    if (c->tma_error) cudaFree(c->tma_error);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -691,6 +810,7 @@ int lbm_create(const lbm_params *p, lbm_ctx **out)
         return fail(nullptr, LBM_ERR_INVALID, "lbm_create: bad z range [%d, %d)", zb, ze);
     switch (p->variant) {
         case LBM_VARIANT_AUTO: case LBM_VARIANT_SCALAR: case LBM_VARIANT_VEC2: case LBM_VARIANT_VEC4: break;
+        case LBM_VARIANT_TMA: break;
         case LBM_VARIANT_AA:
             if (zb != 0 || ze != p->dim)
                 return fail(nullptr, LBM_ERR_INVALID, "lbm_create: the AA variant needs the whole cube on one device");
@@ -753,6 +873,11 @@ int lbm_create(const lbm_params *p, lbm_ctx **out)
     int vec = (p->variant == LBM_VARIANT_AUTO || p->variant == LBM_VARIANT_SCALAR) ? 1 : p->variant;
     c->aa = p->variant == LBM_VARIANT_AA;
     if (c->aa) vec = 1;
+    if (p->variant == LBM_VARIANT_TMA) {
+        vec = 1;
+        // eligibility; otherwise the scalar kernel is used
+        c->tma = p->stride <= p->dim && p->stride * (long long)(p->precision == LBM_F32 ? 4 : 8) >= 16 && p->dim >= 32;
+    }
     if (vec > vmax) vec = vmax;
     while (vec > 1 && (p->stride % vec != 0 || p->dim % vec != 0)) vec /= 2;
     c->vec = vec;
@@ -802,6 +927,11 @@ int lbm_create(const lbm_params *p, lbm_ctx **out)
     if (p->precision == LBM_F32) rc = compute_stale<float>(c, c->cf, c->stale_f);
     else rc = compute_stale<double>(c, c->cd, c->stale_d);
     if (rc != LBM_OK) return bail(rc);
+
+    if (c->tma) {
+        rc = setup_tma(c, prop.multiProcessorCount);
+        if (rc != LBM_OK) return bail(rc);
+    }
 
     *out = c;
     return LBM_OK;
@@ -924,6 +1054,11 @@ int lbm_sync(lbm_ctx *c)
     int rc = use_device(c);
     if (rc != LBM_OK) return rc;
     LBM_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->tma_error) {
+        int flag = 0;
+        LBM_CUDA(c, cudaMemcpy(&flag, c->tma_error, sizeof(int), cudaMemcpyDeviceToHost));
+        if (flag) return fail(c, LBM_ERR_CUDA, "TMA variant: an mbarrier wait timed out (bulk copy never completed)");
+    }
     return LBM_OK;
 }
 

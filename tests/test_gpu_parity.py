@@ -50,7 +50,7 @@ CASES = [
 
 
 @pytest.mark.parametrize("precision", ["f32", "f64"])
-@pytest.mark.parametrize("variant", [0, 1, 2, 4, 8])
+@pytest.mark.parametrize("variant", [0, 1, 2, 4, 8, 16])
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "d%d_s%d_i%d_e%d" % (c[0], c[1], c[4], c[5]))
 def test_strict_matches_oracle(case, variant, precision):
     dim, stride, nu, u_lid, its, every = case
@@ -67,7 +67,7 @@ def test_strict_matches_oracle(case, variant, precision):
 
 
 @pytest.mark.parametrize("precision", ["f32", "f64"])
-@pytest.mark.parametrize("variant", [0, 4, 8])
+@pytest.mark.parametrize("variant", [0, 4, 8, 16])
 @pytest.mark.parametrize("case", CASES[:5], ids=lambda c: "d%d_s%d_i%d_e%d" % (c[0], c[1], c[4], c[5]))
 def test_fast_within_tolerance(case, variant, precision):
     """-o (contracted arithmetic, approximate fp32 division) against the strict oracle."""
@@ -312,3 +312,31 @@ def test_graph_chunks_from_any_parity(every, variant):
             exp_f = st["f_stream"] if (done + 1) % 2 == 0 else st["f_collide"]
             assert s.read_f().tobytes() == exp_f.tobytes(), done
         assert s.iteration == done and s.launch_count == done
+
+
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+@pytest.mark.parametrize("tx", [None, "32", "64"])
+def test_tma_variant_rows_segments_and_slabs(tx, precision, monkeypatch):
+    """The TMA-fed kernels (bulk-tensor loads into an mbarrier ring, bulk-tensor stores): whole rows per
+    tile, rows cut into several segments (edge threads fetch their neighbour themselves), different
+    strides, macro stores, and as the interior kernel of a slab group."""
+    from lbmcl_b200.capi import Group
+    if tx is not None:
+        monkeypatch.setenv("LBM_TMA_TX", tx)
+    dim, its, every = 128, 7, 3
+    for stride in (32, 128, 8):
+        exp = Oracle(precision).run(dim, stride, 0.0089, 0.05, its, every)
+        with _sim(dim=dim, precision=precision, stride=stride, variant=16) as s:
+            rho, u = s.run_snapshots(its, every)
+            got_f = s.read_f()
+        assert rho.tobytes() == exp["rho"].tobytes() and u.tobytes() == exp["u"].tobytes(), stride
+    o = Oracle(precision)
+    st = o.alloc(dim)
+    o.init(st, dim, 8, 0.0089, 0.05)
+    for it in range(1, its + 1):
+        o.step(st, dim, 8, 0.0089, 0.05, it, 0)
+    assert got_f.tobytes() == (st["f_stream"] if (its + 1) % 2 == 0 else st["f_collide"]).tobytes()
+    exp = Oracle(precision).run(64, 32, 0.0089, 0.05, 9, 3)
+    with Group([0, 0, 0, 0], dim=64, precision=precision, stride=32, variant=16) as g:
+        rho, u = g.run_snapshots(9, 3)
+    assert rho.tobytes() == exp["rho"].tobytes() and u.tobytes() == exp["u"].tobytes()
