@@ -209,10 +209,11 @@ class Simulation:
         self._check(self.lib.lbm_set_stream(self.h, ctypes.c_void_p(cuda_stream_ptr)))
 
     def read_macros(self, rho=None, u=None):
+        """rho[N], u[3, N] in the reference's global layouts.  With both arguments omitted fresh arrays
+        are allocated; if only one array is given, only that field is read."""
         n = self.dim ** 3
-        if rho is None:
+        if rho is None and u is None:
             rho = np.full(n, np.nan, dtype=self.dtype)
-        if u is None:
             u = np.full((3, n), np.nan, dtype=self.dtype)
         self._check(self.lib.lbm_read_macros(self.h, _ptr(rho), _ptr(u)))
         return rho, u
@@ -383,9 +384,8 @@ class Group:
 
     def read_macros(self, rho=None, u=None):
         n = self.dim ** 3
-        if rho is None:
+        if rho is None and u is None:
             rho = np.full(n, np.nan, dtype=self.dtype)
-        if u is None:
             u = np.full((3, n), np.nan, dtype=self.dtype)
         self._check(self.lib.lbm_group_read_macros(self.h, _ptr(rho), _ptr(u)))
         return rho, u
