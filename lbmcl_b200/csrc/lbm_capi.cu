@@ -301,15 +301,13 @@ cudaError_t launch_tma_tx(lbm_ctx *c, const StepArgs<T> &sa, const TmaArgs<T> &a
     const bool fast = c->p.fast_math != 0;
     const CUtensorMap &ms = c->tmap[c->cur], &md = c->tmap[c->cur ^ 1];
     (void)sa;
+    // the opt-in to > 48 KB of dynamic shared memory is per function AND per device: set it on every
+    // launch (a host-side table update) rather than caching it per process
 #define LBM_TMA_LAUNCH(F, M)                                                                                    \
     do {                                                                                                        \
-        static bool attr_done = false;                                                                          \
-        if (!attr_done) {                                                                                       \
-            cudaError_t e = cudaFuncSetAttribute(step_tma_kernel<T, F, M, TX>,                                  \
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);     \
-            if (e != cudaSuccess) return e;                                                                     \
-            attr_done = true;                                                                                   \
-        }                                                                                                       \
+        cudaError_t e = cudaFuncSetAttribute(step_tma_kernel<T, F, M, TX>,                                      \
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);         \
+        if (e != cudaSuccess) return e;                                                                         \
         step_tma_kernel<T, F, M, TX><<<grid, TX, c->tma_smem, s>>>(ms, md, a, c->tma_error);                   \
     } while (0)
     if (fast) { if (macro) LBM_TMA_LAUNCH(true, true); else LBM_TMA_LAUNCH(true, false); }
