@@ -55,6 +55,8 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--dense-halos", action="store_true",
+                    help="N > 1: exchange packed halos with ncclSend/ncclRecv instead of fused peer stores")
     return ap.parse_args()
 
 
@@ -222,7 +224,7 @@ def run_b200(a):
     import torch
     import torch.distributed as dist
     from lbmcl_b200.capi import Simulation
-    from lbmcl_b200.slabs import slab_range
+    from lbmcl_b200.slabs import connect_slabs, slab_range
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -255,17 +257,15 @@ def run_b200(a):
     has_lo, has_hi = rank > 0, rank < world - 1
 
     if world > 1:
-        # NCCL communicator owned by the library; torch.distributed only carries the 128-byte id
-        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
-        if rank == 0:
-            uid.copy_(torch.frombuffer(bytearray(Simulation.comm_unique_id()), dtype=torch.uint8))
-        dist.broadcast(uid, 0)
-        sim.comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world)
+        # NCCL communicator owned by the library; torch.distributed only bootstraps it (128-byte id,
+        # CUDA IPC handles of the neighbours' lattices)
+        transport = connect_slabs(sim, rank, world, dev, fused=not a.dense_halos)
 
     def run_steps(n, every=0):
-        # N = 1: n launches of the step kernel.  N > 1: per iteration boundary planes -> pack ->
-        # ncclSend/ncclRecv of the 5 crossing populations per face -> unpack on a high-priority stream,
-        # interior planes concurrently on `main` (lbm_run drives it, see include/lbm_b200.h 2b)
+        # N = 1: n launches of the step kernel.  N > 1: per iteration the boundary planes run on a
+        # high-priority stream and hand the 5 crossing populations per face to the neighbours (peer
+        # stores over NVLink + an NCCL token, or packed ncclSend/ncclRecv), interior planes concurrently
+        # on `main`; lbm_run drives it (include/lbm_b200.h, transports 2b / 2c)
         sim.run(n, every)
 
     def sync_all():
@@ -339,7 +339,7 @@ def run_b200(a):
             "scaling": "strong", "vs_baseline": None, "dtype": a.precision, "data": "synthetic",
             "config": {
                 "workload": f"LDC {dim}^3 {a.precision}, nu 0.0089, U 0.05, stride {a.stride}, -e 0"
-                            + (f", {world} z-slabs of {nz} planes, NCCL halo exchange" if world > 1 else ""),
+                            + (f", {world} z-slabs of {nz} planes, halo transport {transport}" if world > 1 else ""),
                 "kernel": f"two-lattice pull, {vec} cell(s)/thread, block {list(eff_block)}, "
                           + ("fast math (-o)" if a.fast_math else "strict IEEE operation order"),
                 "l2": "lattices (2 x %.2f GB per GPU) exceed the 126 MB L2; no flush needed"

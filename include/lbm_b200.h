@@ -216,6 +216,21 @@ int lbm_halo_unpack(lbm_ctx *ctx);
 int lbm_comm_unique_id(uint8_t id[LBM_COMM_ID_BYTES]);
 int lbm_comm_init(lbm_ctx *ctx, const uint8_t id[LBM_COMM_ID_BYTES], int rank, int world);
 
+/* (2c) fused exchange between processes.  lbm_ipc_export() describes this context's two lattices
+ * (CUDA IPC memory handles + geometry, LBM_IPC_HANDLE_BYTES opaque bytes); the host ships the blob to
+ * the neighbouring ranks, which call lbm_ipc_attach(ctx, face, blob_of_the_neighbour_on_that_face).
+ * When every interior face of a context with a communicator (2b) is attached and lbm_comm_fused(ctx, 1)
+ * has been called, lbm_run() lets the boundary-plane kernels store the crossing populations straight into the neighbours' halo planes over
+ * NVLink -- no pack, no unpack, no bulk send -- and NCCL only carries a one-word, stream-ordered token
+ * per face and iteration.  If attaching fails (no peer access), the dense NCCL transport stays in use. */
+#define LBM_IPC_HANDLE_BYTES 192
+int lbm_ipc_export(lbm_ctx *ctx, uint8_t blob[LBM_IPC_HANDLE_BYTES]);
+int lbm_ipc_attach(lbm_ctx *ctx, int face, const uint8_t blob[LBM_IPC_HANDLE_BYTES]);
+/* Switch the fused transport on (1) or off (0).  EVERY rank of the communicator must make the same
+ * choice (a rank sending tokens cannot talk to a rank expecting dense halos): the host enables it only
+ * after all ranks have reported successful attachment. */
+int lbm_comm_fused(lbm_ctx *ctx, int enable);
+
 /* Same-process group of slab contexts, ordered by z.  lbm_group_create builds n contexts from one
  * parameter block (z range split evenly over devices[0..n-1]), enables peer access and links
  * neighbours.  The group calls mirror the single-context ones. */

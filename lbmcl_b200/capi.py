@@ -24,7 +24,7 @@ EXPORTS = [
     "lbm_sync", "lbm_read_macros", "lbm_read_macros_slab", "lbm_read_map", "lbm_read_f", "lbm_time_ms", "lbm_device_name",
     "lbm_effective_params", "lbm_block_shape", "lbm_device_bytes", "lbm_launch_count", "lbm_iteration",
     "lbm_set_stream", "lbm_step_planes", "lbm_advance", "lbm_z_range", "lbm_halo_elems", "lbm_halo_send_buffer", "lbm_halo_recv_buffer", "lbm_halo_pack",
-    "lbm_halo_unpack", "lbm_comm_unique_id", "lbm_comm_init", "lbm_group_create", "lbm_group_destroy", "lbm_group_last_error", "lbm_group_size",
+    "lbm_halo_unpack", "lbm_comm_unique_id", "lbm_comm_init", "lbm_ipc_export", "lbm_ipc_attach", "lbm_comm_fused", "lbm_group_create", "lbm_group_destroy", "lbm_group_last_error", "lbm_group_size",
     "lbm_group_ctx", "lbm_group_init", "lbm_group_run", "lbm_group_sync", "lbm_group_read_macros",
     "lbm_group_time_ms",
 ]
@@ -109,6 +109,9 @@ def load() -> ctypes.CDLL:
     lib.lbm_halo_unpack.argtypes = [vp]
     lib.lbm_comm_unique_id.argtypes = [vp]
     lib.lbm_comm_init.argtypes = [vp, vp, ci, ci]
+    lib.lbm_ipc_export.argtypes = [vp, vp]
+    lib.lbm_ipc_attach.argtypes = [vp, ci, vp]
+    lib.lbm_comm_fused.argtypes = [vp, ci]
     lib.lbm_group_create.argtypes = [ctypes.POINTER(LbmParams), ctypes.POINTER(ctypes.c_int32), ci,
                                      ctypes.POINTER(vp)]
     lib.lbm_group_destroy.argtypes = [vp]
@@ -317,6 +320,20 @@ class Simulation:
     def comm_init(self, unique_id: bytes, rank: int, world: int):
         buf = (ctypes.c_uint8 * 128).from_buffer_copy(unique_id)
         self._check(self.lib.lbm_comm_init(self.h, buf, rank, world))
+
+    IPC_BYTES = 192
+
+    def ipc_export(self) -> bytes:
+        buf = (ctypes.c_uint8 * self.IPC_BYTES)()
+        self._check(self.lib.lbm_ipc_export(self.h, buf))
+        return bytes(buf)
+
+    def ipc_attach(self, face: int, blob: bytes):
+        buf = (ctypes.c_uint8 * self.IPC_BYTES).from_buffer_copy(blob)
+        self._check(self.lib.lbm_ipc_attach(self.h, face, buf))
+
+    def comm_fused(self, enable: bool):
+        self._check(self.lib.lbm_comm_fused(self.h, 1 if enable else 0))
 
     def run_snapshots(self, iterations: int, every: int):
         """The schedule of lbmcl.hpp:490-521: snapshot of rho/u after init and after every flagged

@@ -75,8 +75,13 @@ struct lbm_ctx {
     int64_t device_bytes = 0;
     int cur = 0;  // index of the lattice the NEXT iteration reads
 
-    // same-process neighbours (lbm_group)
+    // neighbours whose halo planes this context's boundary kernels write directly (peer stores):
+    // same-process group members (lbm_group) or lattices of other processes opened through CUDA IPC
+    // (lbm_ipc_attach).  peer_f[face][lattice], peer_zs0[face] = global z of the neighbour's plane 0.
     lbm_ctx *peer[2] = {nullptr, nullptr};
+    void *peer_f[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    int peer_zs0[2] = {0, 0};
+    bool peer_ipc[2] = {false, false};
 
     // one process per device: NCCL communicator over the slabs (lbm_comm_init)
     ncclComm_t comm = nullptr;
@@ -85,6 +90,8 @@ struct lbm_ctx {
     cudaEvent_t ev_bk[2] = {nullptr, nullptr};  // boundary kernels of iteration parity p done
     cudaEvent_t ev_in[2] = {nullptr, nullptr};  // interior kernel of iteration parity p done
     cudaEvent_t ev_join = nullptr;
+    int *token = nullptr;                     // 3 ints: sent token, received from above, received from below
+    bool fused = false;                       // lbm_comm_fused(): peer stores + token instead of dense halos
 
     // execution
     cudaStream_t own_stream = nullptr;
@@ -193,16 +200,15 @@ StepArgs<T> make_step_args(lbm_ctx *c, int z_begin, int z_end, const Consts<T> &
     a.u = static_cast<T *>(c->u);
     a.peer_lo = nullptr;
     a.peer_hi = nullptr;
-    if (c->peer[0]) {
-        // my first owned plane is the neighbour's high halo plane, in the lattice it reads next
-        lbm_ctx *n = c->peer[0];
-        a.peer_lo = static_cast<T *>(n->f[n->cur ^ 1]);
-        a.peer_lo_plane = c->z_begin - n->zs0;
+    // my first / last owned plane is the neighbour's high / low halo plane, in the lattice it reads
+    // next (all slabs advance in lock step, so the neighbour's lattice index equals mine)
+    if (c->peer_f[0][0]) {
+        a.peer_lo = static_cast<T *>(c->peer_f[0][c->cur ^ 1]);
+        a.peer_lo_plane = c->z_begin - c->peer_zs0[0];
     }
-    if (c->peer[1]) {
-        lbm_ctx *n = c->peer[1];
-        a.peer_hi = static_cast<T *>(n->f[n->cur ^ 1]);
-        a.peer_hi_plane = (c->z_end - 1) - n->zs0;
+    if (c->peer_f[1][0]) {
+        a.peer_hi = static_cast<T *>(c->peer_f[1][c->cur ^ 1]);
+        a.peer_hi_plane = (c->z_end - 1) - c->peer_zs0[1];
     }
     a.z_own_begin = c->z_begin;
     a.z_own_end = c->z_end;
@@ -578,6 +584,8 @@ int run_slab_with_comm(lbm_ctx *c, int n_iterations, int every)
     const ncclDataType_t dt = c->p.precision == LBM_F32 ? ncclFloat32 : ncclFloat64;
     const size_t count = (size_t)5 * c->dim * c->dim;
     cudaStream_t S = c->stream, B = c->bstream;
+    // fused transport: every interior face has an IPC-attached neighbour
+    const bool fused = c->fused;
     // the boundary stream starts after whatever the main stream was asked to do before
     LBM_CUDA(c, cudaEventRecord(c->ev_join, S));
     LBM_CUDA(c, cudaStreamWaitEvent(B, c->ev_join, 0));
@@ -598,6 +606,21 @@ int run_slab_with_comm(lbm_ctx *c, int n_iterations, int every)
         c->cur ^= 1;
         c->iteration = it;
 
+        if (fused) {
+            // the boundary kernels have already stored the crossing populations in the neighbours' halo
+            // planes (IPC-mapped peer memory); only a stream-ordered token travels through NCCL: the
+            // neighbour's next boundary kernel starts after my boundary kernel has completed
+            ncclResult_t r = n.GroupStart();
+            if (r == ncclSuccess && has_hi) r = n.Send(c->token, 1, ncclInt32, c->comm_rank + 1, c->comm, B);
+            if (r == ncclSuccess && has_hi) r = n.Recv(c->token + 1, 1, ncclInt32, c->comm_rank + 1, c->comm, B);
+            if (r == ncclSuccess && has_lo) r = n.Send(c->token, 1, ncclInt32, c->comm_rank - 1, c->comm, B);
+            if (r == ncclSuccess && has_lo) r = n.Recv(c->token + 2, 1, ncclInt32, c->comm_rank - 1, c->comm, B);
+            const ncclResult_t e = n.GroupEnd();
+            if (r == ncclSuccess) r = e;
+            if (r != ncclSuccess)
+                return fail(c, LBM_ERR_CUDA, "NCCL token exchange failed (%d) - %s", (int)r, n.GetErrorString(r));
+            continue;
+        }
         // exchange on the boundary stream (pack / unpack use c->stream: point it at B for a moment)
         c->stream = B;
         int rc = lbm_halo_pack(c);
@@ -725,6 +748,84 @@ int lbm_comm_init(lbm_ctx *c, const uint8_t id[LBM_COMM_ID_BYTES], int rank, int
     LBM_NCCL(c, n.CommInitRank(&c->comm, world, u, rank));
     c->comm_rank = rank;
     c->comm_world = world;
+    LBM_CUDA(c, cudaMalloc(&c->token, 3 * sizeof(int)));
+    LBM_CUDA(c, cudaMemset(c->token, 0, 3 * sizeof(int)));
+    return LBM_OK;
+}
+
+int lbm_comm_fused(lbm_ctx *c, int enable)
+{
+    if (!c) return LBM_ERR_INVALID;
+    if (!enable) {
+        c->fused = false;
+        return LBM_OK;
+    }
+    if (!c->comm) return fail(c, LBM_ERR_STATE, "lbm_comm_fused: no communicator (lbm_comm_init)");
+    const bool has_lo = c->z_begin > 0, has_hi = c->z_end < c->dim;
+    if ((has_lo && !c->peer_f[0][0]) || (has_hi && !c->peer_f[1][0]))
+        return fail(c, LBM_ERR_STATE, "lbm_comm_fused: an interior face has no attached neighbour (lbm_ipc_attach)");
+    c->fused = has_lo || has_hi;
+    return LBM_OK;
+}
+
+// ---- CUDA IPC: let a neighbouring PROCESS's boundary kernel store straight into this lattice ----
+namespace {
+struct IpcBlob {
+    cudaIpcMemHandle_t f[2];
+    int32_t zs0, nz_local, dim, precision;
+    int64_t stride, n_alloc;
+};
+static_assert(sizeof(IpcBlob) <= LBM_IPC_HANDLE_BYTES, "IpcBlob must fit LBM_IPC_HANDLE_BYTES");
+}  // namespace
+
+int lbm_ipc_export(lbm_ctx *c, uint8_t out[LBM_IPC_HANDLE_BYTES])
+{
+    if (!c || !out) return LBM_ERR_INVALID;
+    if (c->aa) return fail(c, LBM_ERR_INVALID, "lbm_ipc_export: the AA variant is single-device");
+    int rc = use_device(c);
+    if (rc != LBM_OK) return rc;
+    IpcBlob b{};
+    for (int i = 0; i < 2; ++i) LBM_CUDA(c, cudaIpcGetMemHandle(&b.f[i], c->f[i]));
+    b.zs0 = c->zs0;
+    b.nz_local = c->nz_local;
+    b.dim = c->dim;
+    b.precision = c->p.precision;
+    b.stride = c->p.stride;
+    b.n_alloc = c->n_alloc;
+    std::memset(out, 0, LBM_IPC_HANDLE_BYTES);
+    std::memcpy(out, &b, sizeof b);
+    return LBM_OK;
+}
+
+int lbm_ipc_attach(lbm_ctx *c, int face, const uint8_t in[LBM_IPC_HANDLE_BYTES])
+{
+    if (!c || !in || (face != 0 && face != 1)) return LBM_ERR_INVALID;
+    if (c->peer_f[face][0]) return fail(c, LBM_ERR_STATE, "lbm_ipc_attach: face %d already has a neighbour", face);
+    if ((face == 0 && c->z_begin == 0) || (face == 1 && c->z_end == c->dim))
+        return fail(c, LBM_ERR_INVALID, "lbm_ipc_attach: face %d lies on the cube boundary", face);
+    IpcBlob b;
+    std::memcpy(&b, in, sizeof b);
+    if (b.dim != c->dim || b.precision != c->p.precision || b.stride != c->p.stride)
+        return fail(c, LBM_ERR_INVALID, "lbm_ipc_attach: the neighbour runs a different configuration");
+    // the neighbour must store the plane I write: its halo plane next to my boundary plane
+    const int my_plane = face == 0 ? c->z_begin : c->z_end - 1;
+    if (my_plane < b.zs0 || my_plane >= b.zs0 + b.nz_local)
+        return fail(c, LBM_ERR_INVALID, "lbm_ipc_attach: the neighbour does not store plane %d", my_plane);
+    int rc = use_device(c);
+    if (rc != LBM_OK) return rc;
+    void *p[2] = {nullptr, nullptr};
+    for (int i = 0; i < 2; ++i) {
+        const cudaError_t e = cudaIpcOpenMemHandle(&p[i], b.f[i], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            if (i == 1) cudaIpcCloseMemHandle(p[0]);
+            cudaGetLastError();
+            return fail(c, LBM_ERR_CUDA, "cudaIpcOpenMemHandle(%d) - %s", (int)e, cudaGetErrorName(e));
+        }
+    }
+    c->peer_f[face][0] = p[0];
+    c->peer_f[face][1] = p[1];
+    c->peer_zs0[face] = b.zs0;
+    c->peer_ipc[face] = true;
     return LBM_OK;
 }
 
@@ -759,6 +860,10 @@ void lbm_destroy(lbm_ctx *c)
         if (e.start) cudaEventDestroy(e.start);
         if (e.stop) cudaEventDestroy(e.stop);
     }
+    for (int face = 0; face < 2; ++face)
+        if (c->peer_ipc[face])
+            for (int i = 0; i < 2; ++i)
+                if (c->peer_f[face][i]) cudaIpcCloseMemHandle(c->peer_f[face][i]);
     for (int i = 0; i < 2; ++i)
         if (c->graph_exec[i]) cudaGraphExecDestroy(c->graph_exec[i]);
     if (c->bstream) cudaStreamSynchronize(c->bstream);
@@ -779,6 +884,7 @@ void lbm_destroy(lbm_ctx *c)
     if (c->rho) cudaFree(c->rho);
     if (c->u) cudaFree(c->u);
     if (c->tma_error) cudaFree(c->tma_error);
+    if (c->token) cudaFree(c->token);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -1025,8 +1131,8 @@ int lbm_run(lbm_ctx *c, int n_iterations, int every)
         while (left > 0) {
             const int64_t it = c->iteration + 1;  // 1-based like lbmcl.hpp:435
             // launch-bound lattices: replay a captured chunk of unflagged iterations as one graph
-            if (c->dim <= LBM_GRAPH_MAX_DIM && left >= LBM_GRAPH_CHUNK && c->peer[0] == nullptr &&
-                c->peer[1] == nullptr) {
+            if (c->dim <= LBM_GRAPH_MAX_DIM && left >= LBM_GRAPH_CHUNK && c->peer_f[0][0] == nullptr &&
+                c->peer_f[1][0] == nullptr) {
                 const int64_t last = it + LBM_GRAPH_CHUNK - 1;
                 const bool flagged = every != 0 && (last / every) != ((it - 1) / every);
                 if (!flagged) {

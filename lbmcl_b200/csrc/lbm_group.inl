@@ -118,8 +118,15 @@ int lbm_group_create(const lbm_params *p, const int32_t *devices, int n, lbm_gro
         }
     }
     for (int i = 0; i < n; ++i) {
-        g->ctx[i]->peer[0] = i > 0 ? g->ctx[i - 1] : nullptr;
-        g->ctx[i]->peer[1] = i + 1 < n ? g->ctx[i + 1] : nullptr;
+        for (int face = 0; face < 2; ++face) {
+            lbm_ctx *nb = face == 0 ? (i > 0 ? g->ctx[i - 1] : nullptr) : (i + 1 < n ? g->ctx[i + 1] : nullptr);
+            g->ctx[i]->peer[face] = nb;
+            if (nb) {
+                g->ctx[i]->peer_f[face][0] = nb->f[0];
+                g->ctx[i]->peer_f[face][1] = nb->f[1];
+                g->ctx[i]->peer_zs0[face] = nb->zs0;
+            }
+        }
     }
     g->bstream.assign(n, nullptr);
     g->ev_join.assign(n, nullptr);

@@ -55,3 +55,44 @@ def exchange_halos(send, recv, world: int, rank: int, group=None):
         ops.append(dist.P2POp(dist.isend, send[FACE_LOW], lo, group))
         ops.append(dist.P2POp(dist.irecv, recv[FACE_LOW], lo, group))
     return dist.batch_isend_irecv(ops) if ops else []
+
+
+def connect_slabs(sim, rank: int, world: int, device, fused: bool = True) -> str:
+    """Give the slab context `sim` its library-owned NCCL communicator and, if possible, the fused
+    peer-store transport.  torch.distributed is used only as the bootstrap channel: it broadcasts the
+    128-byte NCCL id, gathers the CUDA IPC blobs and agrees on the transport.  Returns the transport in
+    use: "peer-stores+token" or "nccl-dense"."""
+    import torch
+    import torch.distributed as dist
+    from .capi import LbmError, Simulation
+
+    uid = torch.zeros(128, dtype=torch.uint8, device=device)
+    if rank == 0:
+        uid.copy_(torch.frombuffer(bytearray(Simulation.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(uid, 0)
+    sim.comm_init(uid.cpu().numpy().tobytes(), rank, world)
+    if not fused or world < 2:
+        return "nccl-dense"
+    ok = 1
+    try:
+        blob = torch.frombuffer(bytearray(sim.ipc_export()), dtype=torch.uint8).to(device)
+    except LbmError:
+        blob = torch.zeros(Simulation.IPC_BYTES, dtype=torch.uint8, device=device)
+        ok = 0
+    blobs = [torch.empty_like(blob) for _ in range(world)]
+    dist.all_gather(blobs, blob)
+    lo, hi = neighbours(world, rank)
+    if ok:
+        try:
+            if lo is not None:
+                sim.ipc_attach(FACE_LOW, blobs[lo].cpu().numpy().tobytes())
+            if hi is not None:
+                sim.ipc_attach(FACE_HIGH, blobs[hi].cpu().numpy().tobytes())
+        except LbmError:
+            ok = 0
+    flag = torch.tensor([ok], device=device, dtype=torch.int32)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) == 1:
+        sim.comm_fused(True)
+        return "peer-stores+token"
+    return "nccl-dense"

@@ -12,7 +12,7 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 from lbmcl_b200.capi import Simulation  # noqa: E402
-from lbmcl_b200.slabs import exchange_halos, slab_range  # noqa: E402
+from lbmcl_b200.slabs import connect_slabs, exchange_halos, slab_range  # noqa: E402
 
 
 class DevBuf:
@@ -29,7 +29,9 @@ def main():
     for transport, precision, dim, stride, its in (("host", "f32", 32, 32, 10), ("host", "f64", 64, 32, 6),
                                                    ("nccl-in-library", "f32", 32, 32, 10),
                                                    ("nccl-in-library", "f64", 64, 32, 7),
-                                                   ("nccl-in-library", "f32", 128, 32, 20)):
+                                                   ("nccl-in-library", "f32", 128, 32, 20),
+                                                   ("fused", "f32", 32, 32, 10), ("fused", "f64", 64, 32, 7),
+                                                   ("fused", "f32", 128, 32, 21)):
         z0, z1 = slab_range(dim, world, rank)
         sim = Simulation(dim=dim, precision=precision, stride=stride, device=lr, z_range=(z0, z1))
         main_s = torch.cuda.Stream(device=dev)
@@ -54,11 +56,9 @@ def main():
                     sim.halo_unpack()
         else:
             # library-driven: NCCL communicator inside the context, overlapped schedule in lbm_run
-            uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+            used = connect_slabs(sim, rank, world, dev, fused=(transport == "fused"))
             if rank == 0:
-                uid.copy_(torch.frombuffer(bytearray(Simulation.comm_unique_id()), dtype=torch.uint8))
-            dist.broadcast(uid, 0)
-            sim.comm_init(uid.cpu().numpy().tobytes(), rank, world)
+                print(f"  transport requested {transport}: in use {used}")
             sim.run(its - 3, its)
             sim.run(3, its)
         n = dim ** 3
