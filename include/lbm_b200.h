@@ -140,6 +140,11 @@ int lbm_read_f(lbm_ctx *ctx, void *f_host);
  * Synchronises the context. */
 int lbm_time_ms(lbm_ctx *ctx, double *total_ms, double *kernels_ms);
 
+/* The individual durations behind kernels_ms, in enqueue order: one entry per lbm_step() launch or per
+ * lbm_run() batch -- the per-event list of kernelsTimingsMS() (lbmcl.hpp:580-593).  *count receives the
+ * number of entries; at most `capacity` of them are copied to `out` (may be NULL).  Synchronises. */
+int lbm_launch_times_ms(lbm_ctx *ctx, double *out, int64_t capacity, int64_t *count);
+
 /* CL_DEVICE_NAME (lbmcl.hpp:626, 651). */
 int lbm_device_name(const lbm_ctx *ctx, char *buf, size_t buflen);
 

@@ -21,7 +21,7 @@ VARIANT_AUTO, VARIANT_SCALAR, VARIANT_VEC2, VARIANT_VEC4, VARIANT_AA, VARIANT_TM
 # every symbol include/lbm_b200.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "lbm_default_params", "lbm_create", "lbm_destroy", "lbm_last_error", "lbm_init", "lbm_step", "lbm_run",
-    "lbm_sync", "lbm_read_macros", "lbm_read_macros_slab", "lbm_read_map", "lbm_read_f", "lbm_time_ms", "lbm_device_name",
+    "lbm_sync", "lbm_read_macros", "lbm_read_macros_slab", "lbm_read_map", "lbm_read_f", "lbm_time_ms", "lbm_launch_times_ms", "lbm_device_name",
     "lbm_effective_params", "lbm_block_shape", "lbm_device_bytes", "lbm_launch_count", "lbm_iteration",
     "lbm_set_stream", "lbm_step_planes", "lbm_advance", "lbm_z_range", "lbm_halo_elems", "lbm_halo_send_buffer", "lbm_halo_recv_buffer", "lbm_halo_pack",
     "lbm_halo_unpack", "lbm_comm_unique_id", "lbm_comm_init", "lbm_ipc_export", "lbm_ipc_attach", "lbm_comm_fused", "lbm_group_create", "lbm_group_destroy", "lbm_group_last_error", "lbm_group_size",
@@ -86,6 +86,7 @@ def load() -> ctypes.CDLL:
     lib.lbm_read_map.argtypes = [vp, vp]
     lib.lbm_read_f.argtypes = [vp, vp]
     lib.lbm_time_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+    lib.lbm_launch_times_ms.argtypes = [vp, vp, i64, ctypes.POINTER(i64)]
     lib.lbm_device_name.argtypes = [vp, ctypes.c_char_p, ctypes.c_size_t]
     lib.lbm_effective_params.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
     lib.lbm_block_shape.argtypes = [vp, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]
@@ -246,6 +247,14 @@ class Simulation:
         t, k = ctypes.c_double(), ctypes.c_double()
         self._check(self.lib.lbm_time_ms(self.h, ctypes.byref(t), ctypes.byref(k)))
         return t.value, k.value
+
+    def launch_times_ms(self):
+        """Per-launch (lbm_step) / per-batch (lbm_run) durations in enqueue order."""
+        n = ctypes.c_int64()
+        self._check(self.lib.lbm_launch_times_ms(self.h, None, 0, ctypes.byref(n)))
+        out = np.zeros(n.value, dtype=np.float64)
+        self._check(self.lib.lbm_launch_times_ms(self.h, _ptr(out), n.value, ctypes.byref(n)))
+        return out
 
     @property
     def device_name(self) -> str:

@@ -110,6 +110,7 @@ struct lbm_ctx {
     cudaEvent_t ev_last = nullptr;
     std::vector<EventPair> compute_events;
     double kernels_ms_accum = 0.0;  // folded-in pairs
+    std::vector<float> launch_ms;   // duration of every folded pair, in enqueue order (bounded)
 };
 
 static void lbm_nccl_destroy(ncclComm_t comm);
@@ -1053,6 +1054,7 @@ int lbm_init(lbm_ctx *c)
     }
     c->compute_events.clear();
     c->kernels_ms_accum = 0.0;
+    c->launch_ms.clear();
     LBM_CUDA(c, cudaEventRecord(c->ev_init_start, c->stream));
     if (c->p.precision == LBM_F32) LBM_CUDA(c, launch_init_t<float>(c, c->cf, c->stream));
     else LBM_CUDA(c, launch_init_t<double>(c, c->cd, c->stream));
@@ -1086,6 +1088,7 @@ static int fold_events(lbm_ctx *c, bool all)
         float ms = 0.f;
         LBM_CUDA(c, cudaEventElapsedTime(&ms, e.start, e.stop));
         c->kernels_ms_accum += ms;
+        if (c->launch_ms.size() < (1u << 20)) c->launch_ms.push_back(ms);
         cudaEventDestroy(e.start);
         cudaEventDestroy(e.stop);
     }
@@ -1287,6 +1290,20 @@ int lbm_time_ms(lbm_ctx *c, double *total_ms, double *kernels_ms)
         if ((rc = fold_events(c, true)) != LBM_OK) return rc;
         *kernels_ms = c->kernels_ms_accum;
     }
+    return LBM_OK;
+}
+
+int lbm_launch_times_ms(lbm_ctx *c, double *out, int64_t capacity, int64_t *count)
+{
+    if (!c || !count) return LBM_ERR_INVALID;
+    if (!c->initialised) return fail(c, LBM_ERR_STATE, "lbm_launch_times_ms before lbm_init");
+    int rc = use_device(c);
+    if (rc != LBM_OK) return rc;
+    LBM_CUDA(c, cudaStreamSynchronize(c->stream));
+    if ((rc = fold_events(c, true)) != LBM_OK) return rc;
+    *count = (int64_t)c->launch_ms.size();
+    if (out)
+        for (int64_t i = 0; i < capacity && i < *count; ++i) out[i] = c->launch_ms[(size_t)i];
     return LBM_OK;
 }
 

@@ -413,14 +413,20 @@ public:
         return k;
     }
 
-    // lbmcl.hpp:580-593.  Launches are timed per asynchronous batch here, so the list has the two
-    // aggregate entries rather than one entry per launch.
+    // lbmcl.hpp:580-593: one (name, milliseconds) entry per timed enqueue.  With -f every iteration is
+    // its own launch; otherwise launches are enqueued and timed in asynchronous batches (one entry each).
     std::vector<std::pair<std::string, double>> kernelsTimingsMS()
     {
         std::vector<std::pair<std::string, double>> t;
-        const double k = kernelsTimeMS();
-        t.emplace_back(LBM_INITIALIZE_KERNEL_NAME, totalTimeMS() - k);
-        t.emplace_back(LBM_COMPUTE_KERNEL_NAME, k);
+        if (group) {
+            t.emplace_back(LBM_COMPUTE_KERNEL_NAME, kernelsTimeMS());
+            return t;
+        }
+        int64_t n = 0;
+        check(lbm_launch_times_ms(ctx, nullptr, 0, &n), "time");
+        std::vector<double> ms((size_t)n);
+        if (n > 0) check(lbm_launch_times_ms(ctx, ms.data(), n, &n), "time");
+        for (double v : ms) t.emplace_back(LBM_COMPUTE_KERNEL_NAME, v);
         return t;
     }
 
