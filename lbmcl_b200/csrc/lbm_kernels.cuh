@@ -334,8 +334,13 @@ __global__ void __launch_bounds__(256) step_pull_kernel(const StepArgs<T> a)
         });
     }
 
+    // Warps that lie entirely inside the fluid (interior row, no x-edge cell: 6 of 8 warps per row at
+    // DIM = 256) skip the ghost-constant fix-up and the per-cell classification.
+    const bool all_fluid =
+        __all_sync(mask, rowbits == CT_NONE && x0 >= 2 && x0 + VEC - 1 <= dim - 3) != 0;
+
     // ---- ghost constants for what cells x = 1 / x = DIM-2 would gather from the x walls ----
-    {
+    if (!all_fluid) {
         const int lid = (rowbits & CT_FRONT) ? 1 : 0;  // the gathering cell started with u = (U,0,0)
         constexpr int JL = VEC >= 2 ? 1 : 0;           // x == 1     is element JL of the thread at x0 == XL
         constexpr int XL = VEC >= 2 ? 0 : 1;
@@ -360,7 +365,7 @@ __global__ void __launch_bounds__(256) step_pull_kernel(const StepArgs<T> a)
     T m_rho[VEC], m_ux[VEC], m_uy[VEC], m_uz[VEC];
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
-        const int t = cell_type_from_row(rowbits, x0 + j, dim);
+        const int t = all_fluid ? (int)CT_FLUID : cell_type_from_row(rowbits, x0 + j, dim);
         T fc[Q];
 #pragma unroll
         for (int q = 0; q < Q; ++q) fc[q] = f[q][j];
