@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "liblbm_b200.so")
+LIB_PATH = os.environ.get("LBM_B200_LIB") or os.path.join(HERE, "csrc", "liblbm_b200.so")
 
 ABI_VERSION = 1
 F32, F64 = 0, 1
