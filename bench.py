@@ -358,10 +358,70 @@ def run_b200(a):
         dist.destroy_process_group()
 
 
+def run_b200_single_process(a):
+    """`python bench.py --gpus N` WITHOUT torchrun: one process drives N devices through the same-process
+    z-slab group (lbm_group_*: peer stores between the slabs, event ordering, no NCCL).  The driver's
+    contract launches N > 1 under torchrun (run_b200); this path is what the CLI's -G N uses."""
+    import numpy as np
+    import torch
+    from lbmcl_b200.capi import Group
+
+    if torch.cuda.device_count() < a.gpus:
+        raise SystemExit(f"--gpus {a.gpus} but {torch.cuda.device_count()} device(s) visible")
+    dim = a.dim or 1024
+    esize = 4 if a.precision == "f32" else 8
+    block = tuple(int(v) for v in a.block.split(",")) if a.block else (256, 1, 1)
+    g = Group(list(range(a.gpus)), dim=dim, precision=a.precision, stride=a.stride, block=block, variant=a.variant,
+              fast_math=bool(a.fast_math))
+    g.init()
+    g.run(a.warmup, 0)
+    g.sync()
+    sampler = ClockSampler(0)
+    sampler.start()
+    _, k0 = g.time_ms()
+    g.run(a.steps, 0)
+    _, k1 = g.time_ms()          # slowest slab's device time of the batch (CUDA events on its stream)
+    sampler.stop_flag.set()
+    sampler.join()
+    ms = k1 - k0
+    wet = (dim - 2) ** 3
+    mlups = wet * a.steps / (ms * 1e3)
+    bpc = BYTES_PER_CELL[a.precision]
+    achieved = mlups * 1e6 * bpc / 1e9
+    peak, peak_src = measured_peak()
+    e2e = None
+    if not a.no_e2e:
+        npd = np.float32 if a.precision == "f32" else np.float64
+        rho_h = np.empty(dim ** 3, dtype=npd)
+        t0 = time.perf_counter()
+        g.init()
+        g.run(a.steps, a.steps)
+        g.read_macros(rho_h, None)
+        dt = time.perf_counter() - t0
+        e2e = {"value": wet * a.steps / dt / 1e6, "unit": "MLUPS", "h2d_bytes_per_step": 0,
+               "d2h_bytes_per_step": dim ** 3 * esize / a.steps,
+               "note": "whole job: init + K iterations + blocking rho read-back (pageable host memory)"}
+    out = {
+        "metric": METRIC, "value": mlups, "unit": "MLUPS", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": a.precision, "data": "synthetic",
+        "config": {"workload": f"LDC {dim}^3 {a.precision}, nu 0.0089, U 0.05, stride {a.stride}, -e 0, {a.gpus} z-slabs "
+                               "in one process, halo transport peer-stores+events",
+                   "kernel": "two-lattice pull, strict IEEE operation order" if not a.fast_math else "two-lattice pull, -o"},
+        "roofline": {"bound": "hbm", "achieved": achieved / a.gpus, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / a.gpus / peak, "traffic": None, "peak_source": peak_src, "bytes_per_cell": bpc},
+        "cpu_baseline": None, "e2e": e2e, "gpu_launches": 3 * a.steps * a.gpus, "clocks": sampler.result(),
+    }
+    print(json.dumps(out), flush=True)
+    g.close()
+
+
 def main():
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)
+    elif a.gpus > 1 and int(os.environ.get("WORLD_SIZE", "1")) == 1:
+        run_b200_single_process(a)
     else:
         run_b200(a)
 
