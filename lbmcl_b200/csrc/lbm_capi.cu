@@ -473,6 +473,7 @@ namespace {
 
 constexpr int LBM_GRAPH_CHUNK = 16;     // even: lattice parity and AA step type are restored after a chunk
 constexpr int LBM_GRAPH_MAX_DIM = 64;   // above this one launch takes longer than its enqueue
+constexpr int LBM_GRAPH_MIN_CHUNKS = 8; // replays needed to amortise capture + instantiation
 
 // Enqueue LBM_GRAPH_CHUNK iterations without macro store as ONE graph launch.  The graph is captured
 // on first use for the current parity (source lattice / AA step type) and stream, then replayed.
@@ -1134,7 +1135,12 @@ int lbm_run(lbm_ctx *c, int n_iterations, int every)
         while (left > 0) {
             const int64_t it = c->iteration + 1;  // 1-based like lbmcl.hpp:435
             // launch-bound lattices: replay a captured chunk of unflagged iterations as one graph
-            if (c->dim <= LBM_GRAPH_MAX_DIM && left >= LBM_GRAPH_CHUNK && c->peer_f[0][0] == nullptr &&
+            // (capturing + instantiating a chunk costs a few hundred microseconds of host time: only
+            // worth it when at least LBM_GRAPH_MIN_CHUNKS replays follow, or when the graph exists already)
+            const int gpar = c->aa ? (int)(c->iteration & 1) : c->cur;
+            const bool have_graph = c->graph_exec[gpar] != nullptr && c->graph_stream == c->stream;
+            if (c->dim <= LBM_GRAPH_MAX_DIM && left >= LBM_GRAPH_CHUNK &&
+                (have_graph || left >= LBM_GRAPH_MIN_CHUNKS * LBM_GRAPH_CHUNK) && c->peer_f[0][0] == nullptr &&
                 c->peer_f[1][0] == nullptr) {
                 const int64_t last = it + LBM_GRAPH_CHUNK - 1;
                 const bool flagged = every != 0 && (last / every) != ((it - 1) / every);

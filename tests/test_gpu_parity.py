@@ -302,7 +302,7 @@ def test_graph_chunks_from_any_parity(every, variant):
     with _sim(dim=dim, stride=stride, variant=variant) as s:
         s.init()
         done = 0
-        for n in (5, 40, 1, 35, 16):
+        for n in (5, 40, 131, 1, 160, 35, 16):   # 131/160: graphs get captured (>= 128 left) at either parity, then reused
             s.run(n, every)
             for it in range(done + 1, done + n + 1):
                 o.step(st, dim, stride, nu, u_lid, it, every)
