@@ -340,7 +340,8 @@ def run_b200(a):
             "config": {
                 "workload": f"LDC {dim}^3 {a.precision}, nu 0.0089, U 0.05, stride {a.stride}, -e 0"
                             + (f", {world} z-slabs of {nz} planes, halo transport {transport}" if world > 1 else ""),
-                "kernel": f"two-lattice pull, {vec} cell(s)/thread, block {list(eff_block)}, "
+                "kernel": {8: "in-place AA pattern (one lattice)", 16: "two-lattice pull, TMA-fed"}.get(
+                    a.variant, "two-lattice pull") + f", {vec} cell(s)/thread, block {list(eff_block)}, "
                           + ("fast math (-o)" if a.fast_math else "strict IEEE operation order"),
                 "l2": "lattices (2 x %.2f GB per GPU) exceed the 126 MB L2; no flush needed"
                       % (19 * (nz + 2) * dim * dim * esize / 1e9),
