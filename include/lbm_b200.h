@@ -175,16 +175,17 @@ int lbm_set_stream(lbm_ctx *ctx, void *cuda_stream);
  * extra halo plane per interior face.  Per iteration only the 5 populations that cross a face
  * travel: upward (e_z = +1) q = 6,15,16,17,18 and downward (e_z = -1) q = 5,11,12,13,14.
  *
- * Two transports:
- *  (1) same process, peer access: lbm_link_peers() gives each context its neighbours; lbm_step /
- *      lbm_run on the group then write the crossing populations straight into the neighbour's halo
- *      plane from inside the boundary-plane kernel (NVLink stores) and order the devices with
- *      events.  Use lbm_group_* below.
- *  (2) one process per device (torchrun): the host moves packed halos itself (NCCL send/recv).
- *      lbm_halo_pack() fills the two dense send buffers from the lattice the next iteration reads,
- *      lbm_halo_unpack() scatters the two dense receive buffers into the halo planes.  The four
- *      buffers are DEVICE pointers owned by the context (5*DIM^2 elements each), exposed so that the
- *      host can hand them to its communication library.
+ * Transports (all give the single-device bits):
+ *  (1)  same process (lbm_group_*, CLI -G N): the boundary-plane kernel of a slab stores the crossing
+ *       populations straight into the neighbour's halo plane (NVLink peer stores), the interior runs
+ *       concurrently, devices are ordered with events only;
+ *  (2a) one process per device, host-driven: lbm_step_planes / lbm_advance split the iteration,
+ *       lbm_halo_pack() fills the two dense send buffers from the lattice the next iteration reads,
+ *       lbm_halo_unpack() scatters the two dense receive buffers into the halo planes; the four
+ *       buffers are DEVICE pointers owned by the context (5*DIM^2 elements each), exposed so that the
+ *       host can hand them to its own communication library;
+ *  (2b) one process per device, library-driven dense exchange over NCCL (lbm_comm_*);
+ *  (2c) one process per device, fused: CUDA IPC peer stores as in (1) plus an NCCL token (lbm_ipc_*).
  * ------------------------------------------------------------------------------------------------ */
 
 typedef enum lbm_face { LBM_FACE_LOW = 0, LBM_FACE_HIGH = 1 } lbm_face;
@@ -225,8 +226,8 @@ int lbm_comm_init(lbm_ctx *ctx, const uint8_t id[LBM_COMM_ID_BYTES], int rank, i
  * (CUDA IPC memory handles + geometry, LBM_IPC_HANDLE_BYTES opaque bytes); the host ships the blob to
  * the neighbouring ranks, which call lbm_ipc_attach(ctx, face, blob_of_the_neighbour_on_that_face).
  * When every interior face of a context with a communicator (2b) is attached and lbm_comm_fused(ctx, 1)
- * has been called, lbm_run() lets the boundary-plane kernels store the crossing populations straight into the neighbours' halo planes over
- * NVLink -- no pack, no unpack, no bulk send -- and NCCL only carries a one-word, stream-ordered token
+ * has been called, lbm_run() lets the boundary-plane kernels store the crossing populations straight
+ * into the neighbours' halo planes over NVLink -- no pack, no unpack, no bulk send -- and NCCL only carries a one-word, stream-ordered token
  * per face and iteration.  If attaching fails (no peer access), the dense NCCL transport stays in use. */
 #define LBM_IPC_HANDLE_BYTES 192
 int lbm_ipc_export(lbm_ctx *ctx, uint8_t blob[LBM_IPC_HANDLE_BYTES]);
