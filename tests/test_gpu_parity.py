@@ -340,3 +340,20 @@ def test_tma_variant_rows_segments_and_slabs(tx, precision, monkeypatch):
     with Group([0, 0, 0, 0], dim=64, precision=precision, stride=32, variant=16) as g:
         rho, u = g.run_snapshots(9, 3)
     assert rho.tobytes() == exp["rho"].tobytes() and u.tobytes() == exp["u"].tobytes()
+
+
+def test_per_launch_timings_like_the_reference_event_list():
+    """lbm_launch_times_ms = the per-event list behind kernelsTimingsMS (lbmcl.hpp:580-593): one entry
+    per lbm_step launch / per lbm_run batch, summing to kernels_ms."""
+    with _sim(dim=64, stride=32) as s:
+        s.init()
+        for _ in range(7):
+            s.step(False)
+        s.run(5, 0)
+        t = s.launch_times_ms()
+        total, kernels = s.time_ms()
+        assert len(t) == 8 and np.all(t > 0)
+        assert abs(t.sum() - kernels) < 1e-6 * max(1.0, kernels)
+        assert total >= kernels
+        s.init()                       # a fresh profile, like a fresh LBMCL object
+        assert len(s.launch_times_ms()) == 0

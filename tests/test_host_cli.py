@@ -178,3 +178,37 @@ def test_make_testall_dumps(tmp_path):
         assert open(os.path.join(res2, f"f_{it}.dump")).read() == _expected_f_dump(src, dim, stride), it
         if it >= 1:
             o.step(st, dim, stride, 0.0089, 0.05, it, 1)
+
+
+@pytest.mark.gpu
+def test_in_place_flag_matches_oracle(tmp_path):
+    """-A / --aa: the in-place kernels through the CLI give the same VTI values."""
+    from oracle import Oracle
+    res = str(tmp_path)
+    r = _run("-D", "0", "-d", "32", "-i", "9", "-e", "3", "-s", "32", "--aa", "-v", res, "-p", res)
+    assert r.returncode == 0, r.stderr
+    assert "in-place AA" in r.stdout
+    exp = Oracle("f32").run(32, 32, 0.0089, 0.05, 9, 3)
+    for k, d in enumerate(_read_all(res, 9, 3)):
+        assert d["arrays"]["rho"].tobytes() == np.ascontiguousarray(wet(exp["rho"][k], 32)).tobytes()
+        v = np.moveaxis(wet(exp["u"][k], 32), 0, -1).reshape(-1, 3)
+        assert d["arrays"]["v"].tobytes() == np.ascontiguousarray(v).tobytes()
+
+
+@pytest.mark.gpu
+def test_gpus_flag(tmp_path):
+    """-G N: z-slabs over N devices give the same files; asking for more devices than exist fails loudly."""
+    import torch
+    from oracle import Oracle
+    n_dev = torch.cuda.device_count()
+    res = str(tmp_path)
+    r = _run("-D", "0", "-d", "32", "-i", "6", "-e", "6", "-s", "32", "-G", str(n_dev + 1), "-v", res, "-p", res)
+    assert r.returncode != 0 and "device" in r.stderr
+    if n_dev < 2:
+        pytest.skip("one GPU only")
+    r = _run("-D", "0", "-d", "32", "-i", "6", "-e", "6", "-s", "32", "-G", "2", "-v", res, "-p", res)
+    assert r.returncode == 0, r.stderr
+    assert "2 z-slabs" in r.stdout and "2 GPU(s)" in r.stdout
+    exp = Oracle("f32").run(32, 32, 0.0089, 0.05, 6, 6)
+    d = _read_all(res, 6, 6)[1]
+    assert d["arrays"]["rho"].tobytes() == np.ascontiguousarray(wet(exp["rho"][1], 32)).tobytes()
