@@ -1011,7 +1011,17 @@ int lbm_create(const lbm_params *p, lbm_ctx **out)
     const size_t m_bytes = (size_t)c->n_local * c->esize;
     for (int i = 0; i < (c->aa ? 1 : 2); ++i) {
         cudaError_t err = cudaMalloc(&c->f[i], f_bytes);
-        if (cuda_or_bail(err, "cudaMalloc(f)")) return bail(err == cudaErrorMemoryAllocation ? LBM_ERR_OOM : LBM_ERR_CUDA);
+        if (err == cudaErrorMemoryAllocation) {
+            cudaGetLastError();
+            fail(c, LBM_ERR_OOM,
+                 "lbm_create: cudaMalloc of lattice %d (%.1f GB) failed - cudaErrorMemoryAllocation; %s", i,
+                 (double)f_bytes / 1e9,
+                 c->aa ? "split the cube over more GPUs"
+                       : "the in-place variant (-A, LBM_VARIANT_AA) needs one lattice instead of two, or split the "
+                         "cube over more GPUs (-G N)");
+            return bail(LBM_ERR_OOM);
+        }
+        if (cuda_or_bail(err, "cudaMalloc(f)")) return bail(LBM_ERR_CUDA);
         c->device_bytes += (int64_t)f_bytes;
     }
     {
