@@ -421,7 +421,7 @@ int compute_stale(lbm_ctx *c, const Consts<T> &k, T (&stale)[2][Q])
 // CUDA block of the step kernel.  Constraints: powers of two, bx*VEC | DIM, by | DIM, at most 256
 // threads (the kernels are compiled with __launch_bounds__(256)).
 //   default            x-major rows: bx = min(DIM/VEC, 256), the rest of the 256 threads in y, then z.
-//                      Measured on B200 (profiles/r01_sweep.md): whole x-rows per block are never worse
+//                      Measured on B200 (profiles/r01_ncu_summary.md, sweeps): whole x-rows per block are never worse
 //                      than any other shape, and shapes with a short x extent (the reference default
 //                      -w 8,8,8) lose coalescing.  The requested work-group size is therefore a hint
 //                      that does not change the shape -- it never changes the results either.
