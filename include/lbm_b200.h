@@ -232,7 +232,10 @@ int lbm_comm_init(lbm_ctx *ctx, const uint8_t id[LBM_COMM_ID_BYTES], int rank, i
 #define LBM_IPC_HANDLE_BYTES 192
 int lbm_ipc_export(lbm_ctx *ctx, uint8_t blob[LBM_IPC_HANDLE_BYTES]);
 int lbm_ipc_attach(lbm_ctx *ctx, int face, const uint8_t blob[LBM_IPC_HANDLE_BYTES]);
-/* Switch the fused transport on (1) or off (0).  EVERY rank of the communicator must make the same
+/* (With the fused transport, re-initialising -- lbm_init on every rank -- is safe without a host
+ * barrier: the first lbm_run after it starts with a token exchange, so no rank stores into a
+ * neighbour's halo plane before that neighbour's `initialize` kernel has finished.)
+ * Switch the fused transport on (1) or off (0).  EVERY rank of the communicator must make the same
  * choice (a rank sending tokens cannot talk to a rank expecting dense halos): the host enables it only
  * after all ranks have reported successful attachment. */
 int lbm_comm_fused(lbm_ctx *ctx, int enable);

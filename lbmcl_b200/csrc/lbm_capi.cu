@@ -591,6 +591,23 @@ int run_slab_with_comm(lbm_ctx *c, int n_iterations, int every)
     // the boundary stream starts after whatever the main stream was asked to do before
     LBM_CUDA(c, cudaEventRecord(c->ev_join, S));
     LBM_CUDA(c, cudaStreamWaitEvent(B, c->ev_join, 0));
+    // one word to / from each neighbour, stream-ordered on B
+    auto exchange_tokens = [&]() -> ncclResult_t {
+        ncclResult_t r = n.GroupStart();
+        if (r == ncclSuccess && has_hi) r = n.Send(c->token, 1, ncclInt32, c->comm_rank + 1, c->comm, B);
+        if (r == ncclSuccess && has_hi) r = n.Recv(c->token + 1, 1, ncclInt32, c->comm_rank + 1, c->comm, B);
+        if (r == ncclSuccess && has_lo) r = n.Send(c->token, 1, ncclInt32, c->comm_rank - 1, c->comm, B);
+        if (r == ncclSuccess && has_lo) r = n.Recv(c->token + 2, 1, ncclInt32, c->comm_rank - 1, c->comm, B);
+        const ncclResult_t e = n.GroupEnd();
+        return r == ncclSuccess ? e : r;
+    };
+    if (fused && c->iteration == 0) {
+        // first iteration after lbm_init: my boundary kernel will store into the neighbours' halo planes,
+        // which their `initialize` kernels also write -- wait until the neighbours' initialisation is done
+        const ncclResult_t r = exchange_tokens();
+        if (r != ncclSuccess)
+            return fail(c, LBM_ERR_CUDA, "NCCL token exchange failed (%d) - %s", (int)r, n.GetErrorString(r));
+    }
     for (int i = 0; i < n_iterations; ++i) {
         const int64_t it = c->iteration + 1;
         const bool macro = every != 0 && (it % every) == 0;
@@ -612,13 +629,7 @@ int run_slab_with_comm(lbm_ctx *c, int n_iterations, int every)
             // the boundary kernels have already stored the crossing populations in the neighbours' halo
             // planes (IPC-mapped peer memory); only a stream-ordered token travels through NCCL: the
             // neighbour's next boundary kernel starts after my boundary kernel has completed
-            ncclResult_t r = n.GroupStart();
-            if (r == ncclSuccess && has_hi) r = n.Send(c->token, 1, ncclInt32, c->comm_rank + 1, c->comm, B);
-            if (r == ncclSuccess && has_hi) r = n.Recv(c->token + 1, 1, ncclInt32, c->comm_rank + 1, c->comm, B);
-            if (r == ncclSuccess && has_lo) r = n.Send(c->token, 1, ncclInt32, c->comm_rank - 1, c->comm, B);
-            if (r == ncclSuccess && has_lo) r = n.Recv(c->token + 2, 1, ncclInt32, c->comm_rank - 1, c->comm, B);
-            const ncclResult_t e = n.GroupEnd();
-            if (r == ncclSuccess) r = e;
+            const ncclResult_t r = exchange_tokens();
             if (r != ncclSuccess)
                 return fail(c, LBM_ERR_CUDA, "NCCL token exchange failed (%d) - %s", (int)r, n.GetErrorString(r));
             continue;
