@@ -1129,10 +1129,17 @@ int lbm_step(lbm_ctx *c, int update_macro)
     if ((rc = push_pair(c, &ep)) != LBM_OK) return rc;
     c->compute_events.push_back(ep);
     LBM_CUDA(c, cudaEventRecord(ep.start, c->stream));
-    LBM_CUDA(c, launch_step(c, c->z_begin, c->z_end, update_macro != 0, c->stream));
+    if (c->comm) {
+        // a slab with a communicator always goes through the exchange schedule (one iteration of it)
+        if ((rc = run_slab_with_comm(c, 1, update_macro ? 1 : 0)) != LBM_OK) return rc;
+    } else {
+        if (c->peer_f[0][0] || c->peer_f[1][0])
+            return fail(c, LBM_ERR_STATE, "lbm_step: this slab has peer neighbours; drive it through lbm_group_run");
+        LBM_CUDA(c, launch_step(c, c->z_begin, c->z_end, update_macro != 0, c->stream));
+        c->cur ^= 1;
+        c->iteration += 1;
+    }
     LBM_CUDA(c, cudaEventRecord(ep.stop, c->stream));
-    c->cur ^= 1;
-    c->iteration += 1;
     return record_last(c);
 }
 
@@ -1142,6 +1149,9 @@ int lbm_run(lbm_ctx *c, int n_iterations, int every)
     if (!c->initialised) return fail(c, LBM_ERR_STATE, "lbm_run before lbm_init");
     if (n_iterations < 0 || every < 0) return fail(c, LBM_ERR_INVALID, "lbm_run: negative argument");
     if (n_iterations == 0) return LBM_OK;
+    if (!c->comm && (c->peer_f[0][0] || c->peer_f[1][0]))
+        return fail(c, LBM_ERR_STATE, "lbm_run: this slab has peer neighbours; drive it through lbm_group_run "
+                                      "(same process) or give it a communicator (lbm_comm_init)");
     int rc = use_device(c);
     if (rc != LBM_OK) return rc;
     if ((rc = fold_events(c, false)) != LBM_OK) return rc;
