@@ -212,3 +212,22 @@ def test_gpus_flag(tmp_path):
     exp = Oracle("f32").run(32, 32, 0.0089, 0.05, 6, 6)
     d = _read_all(res, 6, 6)[1]
     assert d["arrays"]["rho"].tobytes() == np.ascontiguousarray(wet(exp["rho"][1], 32)).tobytes()
+
+
+def test_benchmark_aggregation_drops_fastest_and_slowest(tmp_path):
+    """benchmark.sh's aggregation (reference benchmark.sh:109-176): per configuration drop the runs
+    with the smallest and the largest total time, average the rest."""
+    stats = tmp_path / "stats.csv"
+    rows = []
+    for total, kern in ((10.0, 9.0), (30.0, 29.0), (20.0, 19.0), (22.0, 21.0), (18.0, 17.0)):
+        rows.append(f"NVIDIA B200;single;64;50;0;008,008,008;32;1;{total};{kern};{1000 / total};{1000 / kern}")
+    rows.append("NVIDIA B200;single;128;50;0;008,008,008;32;1;5;4;200;250")      # a single run: kept as is
+    stats.write_text("\n".join(rows) + "\n")
+    out = subprocess.run(["awk", "-F;", "-f", os.path.join(HOST, "aggregate.awk"), str(stats)], stdout=subprocess.PIPE,
+                         text=True, check=True).stdout.splitlines()
+    assert out[0].split(";")[:3] == ["device", "precision", "dim"]
+    f = out[1].split(";")
+    assert f[2] == "64" and f[8] == "3"
+    assert abs(float(f[9]) - 20.0) < 1e-9 and abs(float(f[10]) - 19.0) < 1e-9          # mean of 20, 22, 18
+    g = out[2].split(";")
+    assert g[2] == "128" and g[8] == "1" and float(g[9]) == 5.0
