@@ -202,8 +202,13 @@ def test_gpus_flag(tmp_path):
     from oracle import Oracle
     n_dev = torch.cuda.device_count()
     res = str(tmp_path)
-    r = _run("-D", "0", "-d", "32", "-i", "6", "-e", "6", "-s", "32", "-G", str(n_dev + 1), "-v", res, "-p", res)
-    assert r.returncode != 0 and "device" in r.stderr
+    too_many = 1
+    while too_many <= n_dev:
+        too_many *= 2                       # a slab count that divides 32 but exceeds the devices present
+    r = _run("-D", "0", "-d", "32", "-i", "6", "-e", "6", "-s", "32", "-G", str(too_many), "-v", res, "-p", res)
+    assert r.returncode != 0 and "device" in r.stderr, r.stderr
+    r = _run("-D", "0", "-d", "32", "-i", "6", "-e", "6", "-s", "32", "-G", "3", "-v", res, "-p", res)
+    assert r.returncode != 0 and "not divisible" in r.stderr, r.stderr
     if n_dev < 2:
         pytest.skip("one GPU only")
     r = _run("-D", "0", "-d", "32", "-i", "6", "-e", "6", "-s", "32", "-G", "2", "-v", res, "-p", res)
