@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define LBM_B200_ABI_VERSION 1
+#define LBM_B200_ABI_VERSION 2
 
 typedef enum lbm_status {
     LBM_OK = 0,
@@ -52,10 +52,14 @@ typedef enum lbm_variant {
     LBM_VARIANT_VEC4 = 4,   /* two-lattice pull, 4 cells per thread (128-bit fp32 access)        */
     LBM_VARIANT_AA = 8,     /* in-place AA pattern: ONE lattice (half the memory), one cell per
                                thread; whole cube on one device only                             */
-    LBM_VARIANT_TMA = 16    /* two-lattice pull fed by the TMA unit: persistent CTAs, bulk-tensor
+    LBM_VARIANT_TMA = 16,   /* two-lattice pull fed by the TMA unit: persistent CTAs, bulk-tensor
                                loads into an mbarrier ring of row tiles, bulk-tensor stores back;
                                needs stride <= DIM, stride*sizeof(T) >= 16, DIM >= 32 (else the
                                scalar variant is used)                                           */
+    LBM_VARIANT_NVRTC = 32  /* the scalar kernel compiled at run time (NVRTC) with DIM, stride, the
+                               address offsets, INV_TAU and U as literals -- what the reference does
+                               with its -D kernel options (lbmcl.hpp:131-156, CLUtil.hpp:201-229);
+                               single-device launches only, slab launches use the scalar variant    */
 } lbm_variant;
 
 /*
@@ -126,6 +130,18 @@ int lbm_read_macros(lbm_ctx *ctx, void *rho_host, void *u_host);
  * P = (z_end - z_begin) * DIM^2, i.e. only the owned planes, compact. */
 int lbm_read_macros_slab(lbm_ctx *ctx, void *rho_slab, void *u_slab);
 
+/* Asynchronous read-back for hosts that overlap output with computation (the reference's "Total MLUPS"
+ * includes read-back and VTI writing, lbmcl.hpp:261-334, 548-556, 604-607).
+ * lbm_host_alloc / lbm_host_free: page-locked host memory (the copies below are only asynchronous into it).
+ * lbm_read_macros_async: same layouts as lbm_read_macros; returns at once.  The copy runs on the context's
+ * copy stream after everything enqueued so far; iterations enqueued afterwards run concurrently with it,
+ * except that the next iteration that overwrites rho / u (a flagged one) is ordered after the copy by the
+ * library.  One read may be outstanding per context.  lbm_read_wait blocks until it has completed. */
+int lbm_host_alloc(size_t bytes, void **out);
+void lbm_host_free(void *p);
+int lbm_read_macros_async(lbm_ctx *ctx, void *rho_host, void *u_host);
+int lbm_read_wait(lbm_ctx *ctx);
+
 /* Blocking readback of the cell-type map (lbmcl.hpp:164 inside storeMap), global layout int32[N]. */
 int lbm_read_map(lbm_ctx *ctx, int32_t *map_host);
 
@@ -157,6 +173,12 @@ int lbm_effective_params(const lbm_ctx *ctx, double out[3]);
 int lbm_block_shape(const lbm_ctx *ctx, int32_t block[3], int32_t *cells_per_thread);
 int64_t lbm_device_bytes(const lbm_ctx *ctx);
 
+/* LBM_VARIANT_NVRTC without a device: compile the specialised step kernel for `p` (dim, stride, precision,
+ * fast_math, viscosity, velocity) and hand back the sm_100a cubin -- for SASS inspection (cuobjdump) and to
+ * check on a GPU-less box that the embedded kernel source builds.  *size = cubin bytes; at most `capacity`
+ * bytes are copied to `out` (may be NULL). */
+int lbm_spec_cubin(const lbm_params *p, void *out, size_t capacity, size_t *size);
+
 /* Number of compute-kernel launches enqueued since lbm_init (for benchmark bookkeeping). */
 int64_t lbm_launch_count(const lbm_ctx *ctx);
 
@@ -185,7 +207,11 @@ int lbm_set_stream(lbm_ctx *ctx, void *cuda_stream);
  *       buffers are DEVICE pointers owned by the context (5*DIM^2 elements each), exposed so that the
  *       host can hand them to its own communication library;
  *  (2b) one process per device, library-driven dense exchange over NCCL (lbm_comm_*);
- *  (2c) one process per device, fused: CUDA IPC peer stores as in (1) plus an NCCL token (lbm_ipc_*).
+ *  (2c) one process per device, fused: peer stores as in (1) through CUDA IPC mappings (lbm_ipc_*) and
+ *       in-kernel epoch flags -- ONE kernel launch per iteration and rank does compute + exchange + ordering;
+ *       no NCCL, no second stream, no events in the loop (lbm_comm_fused(ctx, LBM_FUSED_FLAGS));
+ *  (2d) as (2c) but ordered by a one-word NCCL token per face and iteration (LBM_FUSED_TOKEN; the
+ *       round-1 form, kept as the fallback where in-kernel polling is not wanted).
  * ------------------------------------------------------------------------------------------------ */
 
 typedef enum lbm_face { LBM_FACE_LOW = 0, LBM_FACE_HIGH = 1 } lbm_face;
@@ -222,23 +248,34 @@ int lbm_halo_unpack(lbm_ctx *ctx);
 int lbm_comm_unique_id(uint8_t id[LBM_COMM_ID_BYTES]);
 int lbm_comm_init(lbm_ctx *ctx, const uint8_t id[LBM_COMM_ID_BYTES], int rank, int world);
 
-/* (2c) fused exchange between processes.  lbm_ipc_export() describes this context's two lattices
- * (CUDA IPC memory handles + geometry, LBM_IPC_HANDLE_BYTES opaque bytes); the host ships the blob to
- * the neighbouring ranks, which call lbm_ipc_attach(ctx, face, blob_of_the_neighbour_on_that_face).
- * When every interior face of a context with a communicator (2b) is attached and lbm_comm_fused(ctx, 1)
- * has been called, lbm_run() lets the boundary-plane kernels store the crossing populations straight
- * into the neighbours' halo planes over NVLink -- no pack, no unpack, no bulk send -- and NCCL only carries a one-word, stream-ordered token
- * per face and iteration.  If attaching fails (no peer access), the dense NCCL transport stays in use. */
-#define LBM_IPC_HANDLE_BYTES 192
+/* (2c)/(2d) fused exchange.  lbm_ipc_export() describes this context's two lattices and its flag words
+ * (CUDA IPC memory handles + geometry, LBM_IPC_HANDLE_BYTES opaque bytes); the host ships the blob to the
+ * neighbouring ranks, which call lbm_ipc_attach(ctx, face, blob_of_the_neighbour_on_that_face).  The call
+ * checks that the two slabs are adjacent (the neighbour's owned planes end where mine begin).
+ * lbm_peer_attach() is the same for a neighbour context of the SAME process (any device with peer access).
+ * lbm_ipc_detach() closes every mapping again and switches the fused transport off.
+ *
+ * lbm_comm_fused(ctx, mode) selects how a context whose interior faces are all attached runs lbm_run():
+ *   LBM_FUSED_OFF    not fused: dense halos over NCCL if a communicator exists (2b);
+ *   LBM_FUSED_FLAGS  (2c) one launch per iteration: the grid starts with the slab's boundary planes, whose
+ *                    blocks wait -- bounded, LBM_SYNC_TIMEOUT_S, default 20 s; lbm_sync reports a timeout --
+ *                    for the neighbours' previous phase, store the 5 crossing populations per face straight
+ *                    into the neighbours' halo planes over NVLink and publish the new phase in the
+ *                    neighbours' flag words; the interior planes follow in the same grid.  lbm_init is a
+ *                    phase too, so re-initialising needs no host barrier.  Every rank must run the same
+ *                    sequence of lbm_init / iterations; the neighbours must be on other devices (or the
+ *                    grids small enough to be co-resident).  No communicator needed.  lbm_init must follow.
+ *   LBM_FUSED_TOKEN  (2d) boundary planes on a high-priority stream with peer stores, interior concurrently,
+ *                    one NCCL send/recv word per face and iteration; needs lbm_comm_init.
+ * EVERY rank must make the same choice: the host enables a mode only after all ranks have reported
+ * successful attachment (lbmcl_b200/slabs.py::connect_slabs). */
+#define LBM_IPC_HANDLE_BYTES 256
+typedef enum lbm_fused_mode { LBM_FUSED_OFF = 0, LBM_FUSED_FLAGS = 1, LBM_FUSED_TOKEN = 2 } lbm_fused_mode;
 int lbm_ipc_export(lbm_ctx *ctx, uint8_t blob[LBM_IPC_HANDLE_BYTES]);
 int lbm_ipc_attach(lbm_ctx *ctx, int face, const uint8_t blob[LBM_IPC_HANDLE_BYTES]);
-/* (With the fused transport, re-initialising -- lbm_init on every rank -- is safe without a host
- * barrier: the first lbm_run after it starts with a token exchange, so no rank stores into a
- * neighbour's halo plane before that neighbour's `initialize` kernel has finished.)
- * Switch the fused transport on (1) or off (0).  EVERY rank of the communicator must make the same
- * choice (a rank sending tokens cannot talk to a rank expecting dense halos): the host enables it only
- * after all ranks have reported successful attachment. */
-int lbm_comm_fused(lbm_ctx *ctx, int enable);
+int lbm_peer_attach(lbm_ctx *ctx, int face, lbm_ctx *neighbour);
+int lbm_ipc_detach(lbm_ctx *ctx);
+int lbm_comm_fused(lbm_ctx *ctx, int mode);
 
 /* Same-process group of slab contexts, ordered by z.  lbm_group_create builds n contexts from one
  * parameter block (z range split evenly over devices[0..n-1]), enables peer access and links
@@ -253,6 +290,8 @@ int lbm_group_init(lbm_group *g);
 int lbm_group_run(lbm_group *g, int n_iterations, int every);
 int lbm_group_sync(lbm_group *g);
 int lbm_group_read_macros(lbm_group *g, void *rho_host, void *u_host);
+/* lbm_read_f over the slabs of a group (storeF, lbmcl.hpp:206-258): host[19*N], the reference's layout */
+int lbm_group_read_f(lbm_group *g, void *f_host);
 int lbm_group_time_ms(lbm_group *g, double *total_ms, double *kernels_ms);
 
 #ifdef __cplusplus

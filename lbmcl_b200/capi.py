@@ -14,19 +14,22 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("LBM_B200_LIB") or os.path.join(HERE, "csrc", "liblbm_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 F32, F64 = 0, 1
-VARIANT_AUTO, VARIANT_SCALAR, VARIANT_VEC2, VARIANT_VEC4, VARIANT_AA, VARIANT_TMA = 0, 1, 2, 4, 8, 16
+VARIANT_AUTO, VARIANT_SCALAR, VARIANT_VEC2, VARIANT_VEC4, VARIANT_AA, VARIANT_TMA, VARIANT_NVRTC = 0, 1, 2, 4, 8, 16, 32
+FUSED_OFF, FUSED_FLAGS, FUSED_TOKEN = 0, 1, 2
 
 # every symbol include/lbm_b200.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "lbm_default_params", "lbm_create", "lbm_destroy", "lbm_last_error", "lbm_init", "lbm_step", "lbm_run",
-    "lbm_sync", "lbm_read_macros", "lbm_read_macros_slab", "lbm_read_map", "lbm_read_f", "lbm_time_ms", "lbm_launch_times_ms", "lbm_device_name",
-    "lbm_effective_params", "lbm_block_shape", "lbm_device_bytes", "lbm_launch_count", "lbm_iteration",
-    "lbm_set_stream", "lbm_step_planes", "lbm_advance", "lbm_z_range", "lbm_halo_elems", "lbm_halo_send_buffer", "lbm_halo_recv_buffer", "lbm_halo_pack",
-    "lbm_halo_unpack", "lbm_comm_unique_id", "lbm_comm_init", "lbm_ipc_export", "lbm_ipc_attach", "lbm_comm_fused", "lbm_group_create", "lbm_group_destroy", "lbm_group_last_error", "lbm_group_size",
-    "lbm_group_ctx", "lbm_group_init", "lbm_group_run", "lbm_group_sync", "lbm_group_read_macros",
-    "lbm_group_time_ms",
+    "lbm_sync", "lbm_read_macros", "lbm_read_macros_slab", "lbm_host_alloc", "lbm_host_free", "lbm_read_macros_async",
+    "lbm_read_wait", "lbm_read_map", "lbm_read_f", "lbm_time_ms", "lbm_launch_times_ms", "lbm_device_name",
+    "lbm_effective_params", "lbm_block_shape", "lbm_device_bytes", "lbm_spec_cubin", "lbm_launch_count", "lbm_iteration",
+    "lbm_set_stream", "lbm_step_planes", "lbm_advance", "lbm_z_range", "lbm_halo_elems", "lbm_halo_send_buffer",
+    "lbm_halo_recv_buffer", "lbm_halo_pack", "lbm_halo_unpack", "lbm_comm_unique_id", "lbm_comm_init", "lbm_ipc_export",
+    "lbm_ipc_attach", "lbm_peer_attach", "lbm_ipc_detach", "lbm_comm_fused", "lbm_group_create", "lbm_group_destroy",
+    "lbm_group_last_error", "lbm_group_size", "lbm_group_ctx", "lbm_group_init", "lbm_group_run", "lbm_group_sync",
+    "lbm_group_read_macros", "lbm_group_read_f", "lbm_group_time_ms",
 ]
 
 
@@ -83,6 +86,12 @@ def load() -> ctypes.CDLL:
     lib.lbm_sync.argtypes = [vp]
     lib.lbm_read_macros.argtypes = [vp, vp, vp]
     lib.lbm_read_macros_slab.argtypes = [vp, vp, vp]
+    lib.lbm_host_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(vp)]
+    lib.lbm_host_free.argtypes = [vp]
+    lib.lbm_host_free.restype = None
+    lib.lbm_read_macros_async.argtypes = [vp, vp, vp]
+    lib.lbm_read_wait.argtypes = [vp]
+    lib.lbm_spec_cubin.argtypes = [ctypes.POINTER(LbmParams), vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
     lib.lbm_read_map.argtypes = [vp, vp]
     lib.lbm_read_f.argtypes = [vp, vp]
     lib.lbm_time_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
@@ -112,6 +121,8 @@ def load() -> ctypes.CDLL:
     lib.lbm_comm_init.argtypes = [vp, vp, ci, ci]
     lib.lbm_ipc_export.argtypes = [vp, vp]
     lib.lbm_ipc_attach.argtypes = [vp, ci, vp]
+    lib.lbm_peer_attach.argtypes = [vp, ci, vp]
+    lib.lbm_ipc_detach.argtypes = [vp]
     lib.lbm_comm_fused.argtypes = [vp, ci]
     lib.lbm_group_create.argtypes = [ctypes.POINTER(LbmParams), ctypes.POINTER(ctypes.c_int32), ci,
                                      ctypes.POINTER(vp)]
@@ -126,6 +137,7 @@ def load() -> ctypes.CDLL:
     lib.lbm_group_run.argtypes = [vp, ci, ci]
     lib.lbm_group_sync.argtypes = [vp]
     lib.lbm_group_read_macros.argtypes = [vp, vp, vp]
+    lib.lbm_group_read_f.argtypes = [vp, vp]
     lib.lbm_group_time_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     _lib = lib
     return lib
@@ -330,7 +342,7 @@ class Simulation:
         buf = (ctypes.c_uint8 * 128).from_buffer_copy(unique_id)
         self._check(self.lib.lbm_comm_init(self.h, buf, rank, world))
 
-    IPC_BYTES = 192
+    IPC_BYTES = 256
 
     def ipc_export(self) -> bytes:
         buf = (ctypes.c_uint8 * self.IPC_BYTES)()
@@ -341,8 +353,27 @@ class Simulation:
         buf = (ctypes.c_uint8 * self.IPC_BYTES).from_buffer_copy(blob)
         self._check(self.lib.lbm_ipc_attach(self.h, face, buf))
 
-    def comm_fused(self, enable: bool):
-        self._check(self.lib.lbm_comm_fused(self.h, 1 if enable else 0))
+    def peer_attach(self, face: int, neighbour: "Simulation"):
+        """Same-process neighbour (any device with peer access): its halo plane becomes a store target."""
+        self._check(self.lib.lbm_peer_attach(self.h, face, neighbour.h))
+
+    def ipc_detach(self):
+        self._check(self.lib.lbm_ipc_detach(self.h))
+
+    def comm_fused(self, mode=FUSED_FLAGS):
+        """FUSED_OFF / FUSED_FLAGS (in-kernel epoch flags, one launch per iteration) / FUSED_TOKEN (NCCL token)."""
+        if mode is True:
+            mode = FUSED_FLAGS
+        elif mode is False:
+            mode = FUSED_OFF
+        self._check(self.lib.lbm_comm_fused(self.h, int(mode)))
+
+    # -- asynchronous read-back into page-locked host memory --
+    def read_macros_async(self, rho, u):
+        self._check(self.lib.lbm_read_macros_async(self.h, _ptr(rho), _ptr(u)))
+
+    def read_wait(self):
+        self._check(self.lib.lbm_read_wait(self.h))
 
     def run_snapshots(self, iterations: int, every: int):
         """The schedule of lbmcl.hpp:490-521: snapshot of rho/u after init and after every flagged
@@ -416,6 +447,11 @@ class Group:
         self._check(self.lib.lbm_group_read_macros(self.h, _ptr(rho), _ptr(u)))
         return rho, u
 
+    def read_f(self):
+        f = np.zeros(19 * self.dim ** 3, dtype=self.dtype)
+        self._check(self.lib.lbm_group_read_f(self.h, _ptr(f)))
+        return f
+
     def time_ms(self):
         t, k = ctypes.c_double(), ctypes.c_double()
         self._check(self.lib.lbm_group_time_ms(self.h, ctypes.byref(t), ctypes.byref(k)))
@@ -442,3 +478,33 @@ class Group:
                 s += 1
         self.sync()
         return rho[:k], u[:k]
+
+
+def pinned_array(shape, dtype):
+    """numpy array over page-locked host memory from lbm_host_alloc (freed when the array is collected)."""
+    lib = load()
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = ctypes.c_void_p()
+    rc = lib.lbm_host_alloc(n, ctypes.byref(p))
+    if rc != 0:
+        raise LbmError(rc, lib.lbm_last_error(None).decode())
+    buf = (ctypes.c_uint8 * max(n, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    import weakref
+    weakref.finalize(buf, lib.lbm_host_free, p)
+    return arr
+
+
+def spec_cubin(**kw) -> bytes:
+    """The run-time specialised (NVRTC) step kernel for a configuration, compiled without a device."""
+    lib = load()
+    p = make_params(**kw)
+    n = ctypes.c_size_t()
+    rc = lib.lbm_spec_cubin(ctypes.byref(p), None, 0, ctypes.byref(n))
+    if rc != 0:
+        raise LbmError(rc, lib.lbm_last_error(None).decode())
+    buf = (ctypes.c_uint8 * n.value)()
+    rc = lib.lbm_spec_cubin(ctypes.byref(p), buf, n.value, ctypes.byref(n))
+    if rc != 0:
+        raise LbmError(rc, lib.lbm_last_error(None).decode())
+    return bytes(buf)

@@ -1,124 +1,29 @@
 // C ABI of the B200-native D3Q19 collide-and-stream path (see include/lbm_b200.h).
 //
 // This file replaces what the reference's lbmcl.hpp obtains from libs/CLUtil.hpp + cl.hpp: device
-// selection, buffers, kernel launches with the ping-pong binding, readbacks and event timing.
-// There is no CPU fallback anywhere in here: without a CUDA device lbm_create fails.
-#include "../../include/lbm_b200.h"
-
-#include <cuda_runtime.h>
+// selection, buffers, kernel launches with the ping-pong binding, readbacks and event timing -- plus the
+// z-slab transports (new functionality).  Host logic only: the kernels are instantiated in the
+// lbm_launch_*.cu translation units.  There is no CPU fallback anywhere in here: without a CUDA device
+// lbm_create fails.
 #include <dlfcn.h>
-#include <nccl.h>  // types only: the functions are resolved with dlopen (no link-time dependency)
 
 #include <cmath>
-#include <cstdarg>
-#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <new>
-#include <string>
-#include <vector>
 
-#include "lbm_kernels.cuh"
-#include "lbm_tma.cuh"
+#include "lbm_ctx.hpp"
 
 using namespace lbm;
 
 namespace {
 
 thread_local std::string g_create_error;
-
-struct EventPair {
-    cudaEvent_t start = nullptr;
-    cudaEvent_t stop = nullptr;
-};
+using EventPair = LbmEventPair;
 
 }  // namespace
 
-struct lbm_ctx {
-    lbm_params p{};
-    int device = 0;
-    std::string device_name;
-    std::string error;
-
-    // geometry of the slab
-    int dim = 0;
-    int z_begin = 0, z_end = 0;  // owned planes
-    int zs0 = 0;                 // global z of stored plane 0
-    int nz_local = 0;            // stored planes (owned + halos)
-    long long n_local = 0;       // stored cells
-    long long n_alloc = 0;       // stored cells rounded up to a multiple of the stride
-    Layout lay{};
-    int layout_mode = LM_GENERIC;
-    bool aa = false;             // in-place AA variant: only f[0] exists
-    bool tma = false;            // TMA-fed variant: tensor maps of the two lattices
-    CUtensorMap tmap[2];
-    int tma_tx = 0, tma_ns = 0, tma_grid = 0;
-    size_t tma_smem = 0;
-    int *tma_error = nullptr;    // device flag set by a kernel whose mbarrier wait timed out
-    int vec = 1;
-    dim3 block{1, 1, 1};
-    size_t esize = 4;
-
-    // effective constants (after the reference's text round trip)
-    double eff_viscosity = 0, eff_velocity = 0, eff_inv_tau = 0;
-    Consts<float> cf{};
-    Consts<double> cd{};
-    float stale_f[2][Q]{};
-    double stale_d[2][Q]{};
-
-    // device memory
-    void *f[2] = {nullptr, nullptr};  // the two lattices
-    void *rho = nullptr;
-    void *u = nullptr;
-    void *halo_send[2] = {nullptr, nullptr};
-    void *halo_recv[2] = {nullptr, nullptr};
-    int64_t device_bytes = 0;
-    int cur = 0;  // index of the lattice the NEXT iteration reads
-
-    // neighbours whose halo planes this context's boundary kernels write directly (peer stores):
-    // same-process group members (lbm_group) or lattices of other processes opened through CUDA IPC
-    // (lbm_ipc_attach).  peer_f[face][lattice], peer_zs0[face] = global z of the neighbour's plane 0.
-    lbm_ctx *peer[2] = {nullptr, nullptr};
-    void *peer_f[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
-    int peer_zs0[2] = {0, 0};
-    bool peer_ipc[2] = {false, false};
-
-    // one process per device: NCCL communicator over the slabs (lbm_comm_init)
-    ncclComm_t comm = nullptr;
-    int comm_rank = -1, comm_world = 0;
-    cudaStream_t bstream = nullptr;           // high-priority stream: boundary planes + exchange
-    cudaEvent_t ev_bk[2] = {nullptr, nullptr};  // boundary kernels of iteration parity p done
-    cudaEvent_t ev_in[2] = {nullptr, nullptr};  // interior kernel of iteration parity p done
-    cudaEvent_t ev_join = nullptr;
-    int *token = nullptr;                     // 3 ints: sent token, received from above, received from below
-    bool fused = false;                       // lbm_comm_fused(): peer stores + token instead of dense halos
-
-    // execution
-    cudaStream_t own_stream = nullptr;
-    cudaStream_t stream = nullptr;
-    int64_t iteration = 0;
-    int64_t launches = 0;
-    bool initialised = false;
-
-    // CUDA graphs of LBM_GRAPH_CHUNK unflagged iterations for launch-bound (small) lattices,
-    // one per starting parity
-    cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
-    cudaStream_t graph_stream = nullptr;  // the stream the graphs were captured on
-
-    // profiling (the reference's event list, lbmcl.hpp:74)
-    cudaEvent_t ev_init_start = nullptr;
-    cudaEvent_t ev_last = nullptr;
-    std::vector<EventPair> compute_events;
-    double kernels_ms_accum = 0.0;  // folded-in pairs
-    std::vector<float> launch_ms;   // duration of every folded pair, in enqueue order (bounded)
-};
-
-static void lbm_nccl_destroy(ncclComm_t comm);
-static int setup_tma(lbm_ctx *c, int n_sm);
-
-namespace {
-
-int fail(lbm_ctx *ctx, int code, const char *fmt, ...)
+int lbm_fail(lbm_ctx *ctx, int code, const char *fmt, ...)
 {
     char buf[512];
     va_list ap;
@@ -130,13 +35,12 @@ int fail(lbm_ctx *ctx, int code, const char *fmt, ...)
     return code;
 }
 
-#define LBM_CUDA(ctx, ...)                                                                              \
-    do {                                                                                                \
-        cudaError_t e__ = (__VA_ARGS__);                                                                \
-        if (e__ != cudaSuccess)                                                                         \
-            return fail((ctx), e__ == cudaErrorMemoryAllocation ? LBM_ERR_OOM : LBM_ERR_CUDA,           \
-                        "%s:%d %s(%d) - %s", __FILE__, __LINE__, #__VA_ARGS__, (int)e__, cudaGetErrorName(e__)); \
-    } while (0)
+static void lbm_nccl_destroy(ncclComm_t comm);
+static int setup_tma(lbm_ctx *c, int n_sm);
+
+namespace {
+
+#define fail lbm_fail
 
 bool is_pow2(long long v) { return v > 0 && (v & (v - 1)) == 0; }
 int ilog2(long long v)
@@ -152,47 +56,53 @@ int floor_pow2(int v)
     return p;
 }
 
-// lbmcl.hpp:140-141 + kernels.cl:61-62: the value printed with 6 significant digits by operator<<
-// from a T-typed member is what the kernel compiler parses back as a T literal.
-template <typename T>
-T text_roundtrip(double v);
-template <>
-float text_roundtrip<float>(double v)
+// planes of one launch, in grid order: `n_named` individually named planes, then [z_begin, z_end)
+struct Planes {
+    int n_named = 0;
+    int named[2] = {0, 0};
+    int z_begin = 0, z_end = 0;
+    static Planes range(int zb, int ze)
+    {
+        Planes p;
+        p.z_begin = zb;
+        p.z_end = ze > zb ? ze : zb;
+        return p;
+    }
+    int count() const { return n_named + (z_end - z_begin); }
+};
+
+// the boundary planes of a slab (those with a neighbour), deduplicated, and its interior range
+Planes boundary_planes(const lbm_ctx *c)
 {
-    char buf[64];
-    snprintf(buf, sizeof buf, "%g", (double)(float)v);
-    return strtof(buf, nullptr);
+    const bool has_lo = c->z_begin > 0, has_hi = c->z_end < c->dim;
+    const int zlo = c->z_begin, zhi = c->z_end - 1;
+    Planes p;
+    if (has_lo) p.named[p.n_named++] = zlo;
+    if (has_hi && !(has_lo && zhi == zlo)) p.named[p.n_named++] = zhi;
+    return p;
 }
-template <>
-double text_roundtrip<double>(double v)
+Planes interior_planes(const lbm_ctx *c)
 {
-    char buf[64];
-    snprintf(buf, sizeof buf, "%g", v);
-    return strtod(buf, nullptr);
+    const bool has_lo = c->z_begin > 0, has_hi = c->z_end < c->dim;
+    return Planes::range(c->z_begin + (has_lo ? 1 : 0), c->z_end - (has_hi ? 1 : 0));
 }
 
-// Folded in T arithmetic exactly like the reference's compile-time constants.  `volatile` keeps the
-// host compiler from contracting 3*nu + 0.5 into an FMA whatever its flags are.
-template <typename T>
-Consts<T> make_consts(double nu, double u_lid, double *eff)
+SlabSync make_sync(const lbm_ctx *c, unsigned wait_epoch, unsigned signal_epoch)
 {
-    Consts<T> c;
-    volatile T visc = text_roundtrip<T>(nu);
-    volatile T three_nu = T(3.0) * visc;
-    volatile T tau = three_nu + T(0.5);
-    c.u_lid = text_roundtrip<T>(u_lid);
-    c.inv_tau = T(1.0) / tau;
-    c.w[0] = T(1.0) / T(3.0);
-    c.w[1] = T(1.0) / T(18.0);
-    c.w[2] = T(1.0) / T(36.0);
-    eff[0] = (double)visc;
-    eff[1] = (double)c.u_lid;
-    eff[2] = (double)c.inv_tau;
-    return c;
+    SlabSync y{};
+    y.flag_in = reinterpret_cast<unsigned *>(static_cast<char *>(c->f[0]) + c->flag_off);
+    y.flag_out[0] = c->peer_flag[0];
+    y.flag_out[1] = c->peer_flag[1];
+    y.count = c->sync_local;
+    y.error = reinterpret_cast<int *>(c->sync_local + 2);
+    y.wait_epoch = wait_epoch;
+    y.signal_epoch = signal_epoch;
+    y.timeout_ns = c->sync_timeout_ns;
+    return y;
 }
 
 template <typename T>
-StepArgs<T> make_step_args(lbm_ctx *c, int z_begin, int z_end, const Consts<T> &k, const T (&stale)[2][Q])
+StepArgs<T> make_step_args(lbm_ctx *c, const Planes &pl, int peer_mode, const Consts<T> &k, const T (&stale)[2][Q])
 {
     StepArgs<T> a{};
     a.dst = static_cast<T *>(c->f[c->cur ^ 1]);
@@ -202,32 +112,39 @@ StepArgs<T> make_step_args(lbm_ctx *c, int z_begin, int z_end, const Consts<T> &
     a.peer_lo = nullptr;
     a.peer_hi = nullptr;
     // my first / last owned plane is the neighbour's high / low halo plane, in the lattice it reads
-    // next (all slabs advance in lock step, so the neighbour's lattice index equals mine)
-    if (c->peer_f[0][0]) {
-        a.peer_lo = static_cast<T *>(c->peer_f[0][c->cur ^ 1]);
-        a.peer_lo_plane = c->z_begin - c->peer_zs0[0];
-    }
-    if (c->peer_f[1][0]) {
-        a.peer_hi = static_cast<T *>(c->peer_f[1][c->cur ^ 1]);
-        a.peer_hi_plane = (c->z_end - 1) - c->peer_zs0[1];
+    // next (all slabs advance in lock step, so the neighbour's lattice index equals mine).  Launches
+    // that do not hand populations to a neighbour (interior planes, dense-halo transports) get none.
+    if (peer_mode != PEER_NONE) {
+        if (c->peer_f[0][0]) {
+            a.peer_lo = static_cast<T *>(c->peer_f[0][c->cur ^ 1]);
+            a.peer_lo_plane = c->z_begin - c->peer_zs0[0];
+        }
+        if (c->peer_f[1][0]) {
+            a.peer_hi = static_cast<T *>(c->peer_f[1][c->cur ^ 1]);
+            a.peer_hi_plane = (c->z_end - 1) - c->peer_zs0[1];
+        }
     }
     a.z_own_begin = c->z_begin;
     a.z_own_end = c->z_end;
     a.dim = c->dim;
     a.zs0 = c->zs0;
-    a.z_begin = z_begin;
-    a.z_end = z_end;
+    a.zmap_n = pl.n_named;
+    a.zmap0 = pl.named[0];
+    a.zmap1 = pl.named[1];
+    a.z_begin = pl.z_begin;
+    a.z_end = pl.z_end;
     a.n_local = c->n_local;
     a.lay = c->lay;
     a.c = k;
     for (int i = 0; i < 2; ++i)
         for (int q = 0; q < Q; ++q) a.stale[i][q] = stale[i][q];
+    const int lm = peer_mode != PEER_NONE ? c->layout_natural : c->layout_mode;
     const long long S = c->lay.qpitch(), dim = c->dim, plane = dim * dim, es = (long long)sizeof(T);
     for (int q = 0; q < Q; ++q) {
         a.soff[q] = q * S * es;
         const long long dcell = (long long)ey(q) * dim + (long long)ez(q) * plane;  // cells between the two rows
-        const long long rowmul = c->layout_mode == LM_ROWS ? Q : 1;                  // CSoA rows hold Q values per cell
-        if (c->layout_mode == LM_GENERIC) {
+        const long long rowmul = lm == LM_ROWS ? Q : 1;                             // CSoA rows hold Q values per cell
+        if (lm == LM_GENERIC || lm == LM_BLOCKROWS) {
             a.goff[q] = a.poff[q] = 0;
         } else if (c->aa) {
             a.goff[q] = (opp(q) * S - rowmul * dcell) * es;  // SHIFT step: read (c - e_q, opp(q))
@@ -244,165 +161,116 @@ StepArgs<T> make_step_args(lbm_ctx *c, int z_begin, int z_end, const Consts<T> &
     return a;
 }
 
-template <typename T, int VEC>
-cudaError_t launch_step_t(lbm_ctx *c, const StepArgs<T> &a, bool macro, bool peer, cudaStream_t s)
+LaunchCfg launch_cfg(const lbm_ctx *c, int peer_mode)
 {
-    const int nz = a.z_end - a.z_begin;
-    if (nz <= 0) return cudaSuccess;
-    const dim3 b = c->block;
-    const dim3 g((unsigned)(c->dim / (b.x * VEC)), (unsigned)(c->dim / b.y), (unsigned)((nz + b.z - 1) / b.z));
-    const bool fast = c->p.fast_math != 0;
-#define LBM_LAUNCH_LM(F, M, P)                                                                   \
-    do {                                                                                          \
-        if (c->layout_mode == LM_ROWS) step_pull_kernel<T, VEC, F, M, P, LM_ROWS><<<g, b, 0, s>>>(a);     \
-        else if (c->layout_mode == LM_SOA) step_pull_kernel<T, VEC, F, M, P, LM_SOA><<<g, b, 0, s>>>(a);  \
-        else step_pull_kernel<T, VEC, F, M, P, LM_GENERIC><<<g, b, 0, s>>>(a);                    \
-    } while (0)
-#define LBM_LAUNCH(F, M, P) LBM_LAUNCH_LM(F, M, P)
-    if (peer) {
-        if (fast) { if (macro) LBM_LAUNCH(true, true, true); else LBM_LAUNCH(true, false, true); }
-        else      { if (macro) LBM_LAUNCH(false, true, true); else LBM_LAUNCH(false, false, true); }
-    } else {
-        if (fast) { if (macro) LBM_LAUNCH(true, true, false); else LBM_LAUNCH(true, false, false); }
-        else      { if (macro) LBM_LAUNCH(false, true, false); else LBM_LAUNCH(false, false, false); }
-    }
-#undef LBM_LAUNCH
-#undef LBM_LAUNCH_LM
-    c->launches += 1;
-    return cudaGetLastError();
+    LaunchCfg k;
+    k.block = c->block;
+    k.dim = c->dim;
+    k.lm = peer_mode != PEER_NONE ? c->layout_natural : c->layout_mode;
+    k.fast = c->p.fast_math != 0;
+    return k;
 }
 
-// AA variant: iteration `it` (1-based) is a LOCAL step when odd, a SHIFT step when even.
-template <typename T>
-cudaError_t launch_aa_t(lbm_ctx *c, const StepArgs<T> &a, bool macro, cudaStream_t s)
+cudaError_t launch_pull(lbm_ctx *c, const StepArgs<float> &a, bool macro, int peer, cudaStream_t s)
 {
-    const int nz = a.z_end - a.z_begin;
-    if (nz <= 0) return cudaSuccess;
-    const dim3 b = c->block;
-    const dim3 g((unsigned)(c->dim / b.x), (unsigned)(c->dim / b.y), (unsigned)((nz + b.z - 1) / b.z));
-    const bool fast = c->p.fast_math != 0;
-    const bool shift = ((c->iteration + 1) % 2) == 0;
-#define LBM_AA_LM(F, M, SH)                                                                       \
-    do {                                                                                          \
-        if (c->layout_mode == LM_ROWS) step_aa_kernel<T, F, M, SH, LM_ROWS><<<g, b, 0, s>>>(a);   \
-        else if (c->layout_mode == LM_SOA) step_aa_kernel<T, F, M, SH, LM_SOA><<<g, b, 0, s>>>(a); \
-        else step_aa_kernel<T, F, M, SH, LM_GENERIC><<<g, b, 0, s>>>(a);                          \
-    } while (0)
-#define LBM_AA(F, M)                           \
-    do {                                       \
-        if (shift) LBM_AA_LM(F, M, true);      \
-        else LBM_AA_LM(F, M, false);           \
-    } while (0)
-    if (fast) { if (macro) LBM_AA(true, true); else LBM_AA(true, false); }
-    else      { if (macro) LBM_AA(false, true); else LBM_AA(false, false); }
-#undef LBM_AA
-#undef LBM_AA_LM
-    c->launches += 1;
-    return cudaGetLastError();
-}
-
-// TMA-fed variant: persistent CTAs over the live rows of [z_begin, z_end).
-template <typename T, int TX>
-cudaError_t launch_tma_tx(lbm_ctx *c, const StepArgs<T> &sa, const TmaArgs<T> &a, bool macro, cudaStream_t s, int grid)
-{
-    const bool fast = c->p.fast_math != 0;
-    const CUtensorMap &ms = c->tmap[c->cur], &md = c->tmap[c->cur ^ 1];
-    (void)sa;
-    // the opt-in to > 48 KB of dynamic shared memory is per function AND per device: set it on every
-    // launch (a host-side table update) rather than caching it per process
-#define LBM_TMA_LAUNCH(F, M)                                                                                    \
-    do {                                                                                                        \
-        cudaError_t e = cudaFuncSetAttribute(step_tma_kernel<T, F, M, TX>,                                      \
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);         \
-        if (e != cudaSuccess) return e;                                                                         \
-        step_tma_kernel<T, F, M, TX><<<grid, TX, c->tma_smem, s>>>(ms, md, a, c->tma_error);                   \
-    } while (0)
-    if (fast) { if (macro) LBM_TMA_LAUNCH(true, true); else LBM_TMA_LAUNCH(true, false); }
-    else      { if (macro) LBM_TMA_LAUNCH(false, true); else LBM_TMA_LAUNCH(false, false); }
-#undef LBM_TMA_LAUNCH
-    c->launches += 1;
-    return cudaGetLastError();
-}
-
-template <typename T>
-cudaError_t launch_tma_t(lbm_ctx *c, const StepArgs<T> &sa, bool macro, cudaStream_t s)
-{
-    // live planes of this launch
-    const int zf = sa.z_begin < 1 ? 1 : sa.z_begin;
-    const int zl = sa.z_end > c->dim - 1 ? c->dim - 1 : sa.z_end;
-    if (zl <= zf) return cudaSuccess;
-    TmaArgs<T> a{};
-    a.src = sa.src;
-    a.rho = sa.rho;
-    a.u = sa.u;
-    a.dim = c->dim;
-    a.zs0 = c->zs0;
-    a.z_first = zf;
-    a.n_xseg = c->dim / c->tma_tx;
-    a.n_tiles = (zl - zf) * (c->dim - 2) * a.n_xseg;
-    a.ns = c->tma_ns;
-    a.n_local = c->n_local;
-    a.lay = c->lay;
-    a.c = sa.c;
-    for (int i = 0; i < 2; ++i)
-        for (int q = 0; q < Q; ++q) a.stale[i][q] = sa.stale[i][q];
-    const int grid = a.n_tiles < c->tma_grid ? a.n_tiles : c->tma_grid;
-    switch (c->tma_tx) {
-        case 256: return launch_tma_tx<T, 256>(c, sa, a, macro, s, grid);
-        case 128: return launch_tma_tx<T, 128>(c, sa, a, macro, s, grid);
-        case 64: return launch_tma_tx<T, 64>(c, sa, a, macro, s, grid);
-        default: return launch_tma_tx<T, 32>(c, sa, a, macro, s, grid);
+    const LaunchCfg k = launch_cfg(c, peer);
+    switch (c->vec) {
+        case 4: return launch_pull_f32_v4(k, a, macro, peer, s);
+        case 2: return launch_pull_f32_v2(k, a, macro, peer, s);
+        default: return launch_pull_f32_v1(k, a, macro, peer, s);
     }
 }
+cudaError_t launch_pull(lbm_ctx *c, const StepArgs<double> &a, bool macro, int peer, cudaStream_t s)
+{
+    const LaunchCfg k = launch_cfg(c, peer);
+    switch (c->vec) {
+        case 2: return launch_pull_f64_v2(k, a, macro, peer, s);
+        default: return launch_pull_f64_v1(k, a, macro, peer, s);
+    }
+}
+cudaError_t launch_aa(lbm_ctx *c, const StepArgs<float> &a, bool macro, bool shift, cudaStream_t s)
+{
+    return launch_aa_f32(launch_cfg(c, PEER_NONE), a, macro, shift, s);
+}
+cudaError_t launch_aa(lbm_ctx *c, const StepArgs<double> &a, bool macro, bool shift, cudaStream_t s)
+{
+    return launch_aa_f64(launch_cfg(c, PEER_NONE), a, macro, shift, s);
+}
+cudaError_t launch_tma(const TmaCfg &k, const StepArgs<float> &a, int ns, bool macro, cudaStream_t s)
+{
+    return launch_tma_f32(k, a, ns, macro, s);
+}
+cudaError_t launch_tma(const TmaCfg &k, const StepArgs<double> &a, int ns, bool macro, cudaStream_t s)
+{
+    return launch_tma_f64(k, a, ns, macro, s);
+}
 
 template <typename T>
-cudaError_t launch_step_p(lbm_ctx *c, int z_begin, int z_end, bool macro, cudaStream_t s,
+cudaError_t launch_step_p(lbm_ctx *c, const Planes &pl, bool macro, int peer_mode, const SlabSync *sync, cudaStream_t s,
                           const Consts<T> &k, const T (&stale)[2][Q])
 {
-    const StepArgs<T> a = make_step_args<T>(c, z_begin, z_end, k, stale);
-    if (c->aa) return launch_aa_t<T>(c, a, macro, s);
-    const bool peer0 = (a.peer_lo != nullptr && z_begin <= c->z_begin && c->z_begin < z_end) ||
-                       (a.peer_hi != nullptr && z_begin <= c->z_end - 1 && c->z_end - 1 < z_end);
-    if (c->tma && !peer0) return launch_tma_t<T>(c, a, macro, s);
-    const bool peer = (a.peer_lo != nullptr && z_begin <= c->z_begin && c->z_begin < z_end) ||
-                      (a.peer_hi != nullptr && z_begin <= c->z_end - 1 && c->z_end - 1 < z_end);
-    switch (c->vec) {
-        case 4:
-            if constexpr (sizeof(T) == 4) return launch_step_t<T, 4>(c, a, macro, peer, s);
-            else return cudaErrorInvalidValue;
-        case 2: return launch_step_t<T, 2>(c, a, macro, peer, s);
-        default: return launch_step_t<T, 1>(c, a, macro, peer, s);
+    if (pl.count() <= 0) return cudaSuccess;
+    StepArgs<T> a = make_step_args<T>(c, pl, peer_mode, k, stale);
+    if (sync) a.sync = *sync;
+    // a kernel that overwrites rho / u must not overtake an asynchronous read-back of them
+    if (macro && c->copy_pending) {
+        const cudaError_t e = cudaStreamWaitEvent(s, c->ev_copy_done, 0);
+        if (e != cudaSuccess) return e;
     }
+    c->launches += 1;
+    if (c->aa) return launch_aa(c, a, macro, ((c->iteration + 1) % 2) == 0, s);
+    const bool plain = peer_mode == PEER_NONE && pl.n_named == 0;
+    if (c->spec && plain) return lbm_nvrtc_launch(c, &a, macro, pl.count(), s);
+    if (c->tma && plain) {
+        TmaCfg t{};
+        t.map_src = &c->tmap[c->cur];
+        t.map_dst = &c->tmap[c->cur ^ 1];
+        t.tx = c->tma_tx;
+        t.grid = c->tma_grid;
+        t.smem = c->tma_smem;
+        t.error = c->tma_error;
+        t.fast = c->p.fast_math != 0;
+        return launch_tma(t, a, c->tma_ns, macro, s);
+    }
+    return launch_pull(c, a, macro, peer_mode, s);
 }
 
-// one launch of the step kernel over global planes [z_begin, z_end) (clipped to the computed range)
-cudaError_t launch_step(lbm_ctx *c, int z_begin, int z_end, bool macro, cudaStream_t s)
+// one launch of the step kernel over the given planes
+cudaError_t launch_step(lbm_ctx *c, const Planes &pl, bool macro, int peer_mode, cudaStream_t s,
+                        const SlabSync *sync = nullptr)
 {
-    if (c->p.precision == LBM_F32) return launch_step_p<float>(c, z_begin, z_end, macro, s, c->cf, c->stale_f);
-    return launch_step_p<double>(c, z_begin, z_end, macro, s, c->cd, c->stale_d);
+    if (c->p.precision == LBM_F32) return launch_step_p<float>(c, pl, macro, peer_mode, sync, s, c->cf, c->stale_f);
+    return launch_step_p<double>(c, pl, macro, peer_mode, sync, s, c->cd, c->stale_d);
 }
 
-template <typename T>
-cudaError_t launch_init_t(lbm_ctx *c, const Consts<T> &k, cudaStream_t s)
+cudaError_t launch_init(lbm_ctx *c, cudaStream_t s)
 {
-    InitArgs<T> a{};
-    a.f0 = static_cast<T *>(c->f[0]);
-    a.f1 = static_cast<T *>(c->f[1]);
-    a.rho = static_cast<T *>(c->rho);
-    a.u = static_cast<T *>(c->u);
+    if (c->p.precision == LBM_F32) {
+        InitArgs<float> a{};
+        a.f0 = static_cast<float *>(c->f[0]);
+        a.f1 = static_cast<float *>(c->f[1]);
+        a.rho = static_cast<float *>(c->rho);
+        a.u = static_cast<float *>(c->u);
+        a.dim = c->dim;
+        a.zs0 = c->zs0;
+        a.nz_local = c->nz_local;
+        a.n_local = c->n_local;
+        a.lay = c->lay;
+        a.c = c->cf;
+        return launch_init_f32(a, c->aa, s);
+    }
+    InitArgs<double> a{};
+    a.f0 = static_cast<double *>(c->f[0]);
+    a.f1 = static_cast<double *>(c->f[1]);
+    a.rho = static_cast<double *>(c->rho);
+    a.u = static_cast<double *>(c->u);
     a.dim = c->dim;
     a.zs0 = c->zs0;
     a.nz_local = c->nz_local;
     a.n_local = c->n_local;
     a.lay = c->lay;
-    a.c = k;
-    const int bx = c->dim < 64 ? c->dim : 64;
-    const int by = (256 / bx) < c->dim ? (256 / bx) : c->dim;
-    const dim3 b(bx, by, 1);
-    const dim3 g(c->dim / bx, c->dim / by, c->nz_local);
-    if (c->aa) init_aa_kernel<T><<<g, b, 0, s>>>(a);
-    else init_kernel<T><<<g, b, 0, s>>>(a);
-    return cudaGetLastError();
+    a.c = c->cd;
+    return launch_init_f64(a, c->aa, s);
 }
 
 template <typename T>
@@ -410,11 +278,13 @@ int compute_stale(lbm_ctx *c, const Consts<T> &k, T (&stale)[2][Q])
 {
     T *d = nullptr;
     LBM_CUDA(c, cudaMalloc(&d, sizeof(T) * 2 * Q));
-    stale_kernel<T><<<1, 1, 0, c->stream>>>(k, d);
-    LBM_CUDA(c, cudaGetLastError());
-    LBM_CUDA(c, cudaMemcpyAsync(&stale[0][0], d, sizeof(T) * 2 * Q, cudaMemcpyDeviceToHost, c->stream));
-    LBM_CUDA(c, cudaStreamSynchronize(c->stream));
-    LBM_CUDA(c, cudaFree(d));
+    cudaError_t e;
+    if constexpr (sizeof(T) == 4) e = launch_stale_f32(k, d, c->stream);
+    else e = launch_stale_f64(k, d, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&stale[0][0], d, sizeof(T) * 2 * Q, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    LBM_CUDA(c, e);
     return LBM_OK;
 }
 
@@ -466,6 +336,8 @@ int use_device(lbm_ctx *c)
     return LBM_OK;
 }
 
+bool has_neighbours(const lbm_ctx *c) { return c->peer_f[0][0] != nullptr || c->peer_f[1][0] != nullptr; }
+
 }  // namespace
 
 // ---- CUDA graphs for launch-bound lattices ----
@@ -495,7 +367,7 @@ int launch_graph_chunk(lbm_ctx *c)
         LBM_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
         cudaError_t e = cudaSuccess;
         for (int i = 0; i < LBM_GRAPH_CHUNK && e == cudaSuccess; ++i) {
-            e = launch_step(c, c->z_begin, c->z_end, false, c->stream);
+            e = launch_step(c, Planes::range(c->z_begin, c->z_end), false, PEER_NONE, c->stream);
             c->cur ^= 1;
             c->iteration += 1;
         }
@@ -518,7 +390,6 @@ int launch_graph_chunk(lbm_ctx *c)
 }
 
 }  // namespace
-
 // ---- NCCL, resolved at run time ----
 namespace {
 
@@ -575,8 +446,8 @@ NcclApi &nccl()
                         nccl().GetErrorString ? nccl().GetErrorString(r__) : "?");                      \
     } while (0)
 
-// The overlapped z-slab schedule of one rank (see include/lbm_b200.h, transport 2b).
-//   bstream: wait interior(k-1) -> boundary planes(k) -> [advance] pack -> send/recv -> unpack
+// The overlapped z-slab schedule of one rank with a communicator (include/lbm_b200.h, transports 2b / 2d).
+//   bstream: wait interior(k-1) -> boundary planes(k), ONE launch -> [advance] pack -> send/recv -> unpack
 //   stream : wait boundary kernels(k-1) -> interior planes(k)
 // The events alternate with the iteration parity; everything is enqueued without host synchronisation.
 int run_slab_with_comm(lbm_ctx *c, int n_iterations, int every)
@@ -586,8 +457,9 @@ int run_slab_with_comm(lbm_ctx *c, int n_iterations, int every)
     const ncclDataType_t dt = c->p.precision == LBM_F32 ? ncclFloat32 : ncclFloat64;
     const size_t count = (size_t)5 * c->dim * c->dim;
     cudaStream_t S = c->stream, B = c->bstream;
-    // fused transport: every interior face has an IPC-attached neighbour
+    // token form: every interior face has an attached neighbour, the crossing populations are peer stores
     const bool fused = c->fused;
+    const Planes bp = boundary_planes(c), ip = interior_planes(c);
     // the boundary stream starts after whatever the main stream was asked to do before
     LBM_CUDA(c, cudaEventRecord(c->ev_join, S));
     LBM_CUDA(c, cudaStreamWaitEvent(B, c->ev_join, 0));
@@ -612,21 +484,19 @@ int run_slab_with_comm(lbm_ctx *c, int n_iterations, int every)
         const int64_t it = c->iteration + 1;
         const bool macro = every != 0 && (it % every) == 0;
         const int par = (int)(it & 1), prev = par ^ 1;
-        const int zlo = c->z_begin, zhi = c->z_end - 1;
         LBM_CUDA(c, cudaStreamWaitEvent(B, c->ev_in[prev], 0));
-        if (has_lo) LBM_CUDA(c, launch_step(c, zlo, zlo + 1, macro, B));
-        if (has_hi && !(has_lo && zhi == zlo)) LBM_CUDA(c, launch_step(c, zhi, zhi + 1, macro, B));
+        LBM_CUDA(c, launch_step(c, bp, macro, fused ? PEER_STORE : PEER_NONE, B));
         LBM_CUDA(c, cudaEventRecord(c->ev_bk[par], B));
 
         LBM_CUDA(c, cudaStreamWaitEvent(S, c->ev_bk[prev], 0));
-        LBM_CUDA(c, launch_step(c, zlo + (has_lo ? 1 : 0), c->z_end - (has_hi ? 1 : 0), macro, S));
+        LBM_CUDA(c, launch_step(c, ip, macro, PEER_NONE, S));
         LBM_CUDA(c, cudaEventRecord(c->ev_in[par], S));
 
         c->cur ^= 1;
         c->iteration = it;
 
         if (fused) {
-            // the boundary kernels have already stored the crossing populations in the neighbours' halo
+            // the boundary kernel has already stored the crossing populations in the neighbours' halo
             // planes (IPC-mapped peer memory); only a stream-ordered token travels through NCCL: the
             // neighbour's next boundary kernel starts after my boundary kernel has completed
             const ncclResult_t r = exchange_tokens();
@@ -657,6 +527,29 @@ int run_slab_with_comm(lbm_ctx *c, int n_iterations, int every)
     // the main stream's timeline ends after the last exchange
     LBM_CUDA(c, cudaEventRecord(c->ev_join, B));
     LBM_CUDA(c, cudaStreamWaitEvent(S, c->ev_join, 0));
+    return LBM_OK;
+}
+
+// The z-slab schedule with in-kernel epoch flags (transport 2c): ONE launch per iteration and rank on one
+// stream.  The grid starts with the slab's boundary planes: their blocks wait (bounded) for the neighbours'
+// previous phase, store the crossing populations straight into the neighbours' halo planes and the last
+// block of each face publishes the new phase; the interior planes follow in the same grid and overlap the
+// NVLink traffic.  Ranks can drift apart by at most one iteration; nothing else synchronises them.
+int run_slab_flags(lbm_ctx *c, int n_iterations, int every)
+{
+    Planes all = boundary_planes(c);
+    const Planes ip = interior_planes(c);
+    all.z_begin = ip.z_begin;
+    all.z_end = ip.z_end;
+    for (int i = 0; i < n_iterations; ++i) {
+        const int64_t it = c->iteration + 1;
+        const bool macro = every != 0 && (it % every) == 0;
+        c->phase += 1;
+        const SlabSync y = make_sync(c, c->phase - 1, c->phase);
+        LBM_CUDA(c, launch_step(c, all, macro, PEER_FLAGS, c->stream, &y));
+        c->cur ^= 1;
+        c->iteration = it;
+    }
     return LBM_OK;
 }
 
@@ -711,12 +604,29 @@ static int setup_tma(lbm_ctx *c, int n_sm)
     c->tma_grid = ctas * n_sm;
     LBM_CUDA(c, cudaMalloc(&c->tma_error, sizeof(int)));
     LBM_CUDA(c, cudaMemset(c->tma_error, 0, sizeof(int)));
+    // opt in to the large dynamic shared memory once per device (never inside a stream capture)
+    LBM_CUDA(c, tma_prepare(c->device));
     return LBM_OK;
 }
 
 static void lbm_nccl_destroy(ncclComm_t comm)
 {
     if (comm && nccl().CommDestroy) nccl().CommDestroy(comm);
+}
+
+// stream / events of the two-stream slab schedules
+static int ensure_boundary_stream(lbm_ctx *c)
+{
+    if (c->bstream) return LBM_OK;
+    int lo = 0, hi = 0;
+    LBM_CUDA(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    LBM_CUDA(c, cudaStreamCreateWithPriority(&c->bstream, cudaStreamNonBlocking, hi));
+    for (int i = 0; i < 2; ++i) {
+        LBM_CUDA(c, cudaEventCreateWithFlags(&c->ev_bk[i], cudaEventDisableTiming));
+        LBM_CUDA(c, cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
+    }
+    LBM_CUDA(c, cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    return LBM_OK;
 }
 
 extern "C" {
@@ -748,14 +658,7 @@ int lbm_comm_init(lbm_ctx *c, const uint8_t id[LBM_COMM_ID_BYTES], int rank, int
     if (!n.error.empty()) return fail(c, LBM_ERR_CUDA, "lbm_comm_init: %s", n.error.c_str());
     int rc = use_device(c);
     if (rc != LBM_OK) return rc;
-    int lo = 0, hi = 0;
-    LBM_CUDA(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    LBM_CUDA(c, cudaStreamCreateWithPriority(&c->bstream, cudaStreamNonBlocking, hi));
-    for (int i = 0; i < 2; ++i) {
-        LBM_CUDA(c, cudaEventCreateWithFlags(&c->ev_bk[i], cudaEventDisableTiming));
-        LBM_CUDA(c, cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
-    }
-    LBM_CUDA(c, cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    if ((rc = ensure_boundary_stream(c)) != LBM_OK) return rc;
     ncclUniqueId u;
     std::memcpy(&u, id, sizeof u);
     LBM_NCCL(c, n.CommInitRank(&c->comm, world, u, rank));
@@ -763,22 +666,36 @@ int lbm_comm_init(lbm_ctx *c, const uint8_t id[LBM_COMM_ID_BYTES], int rank, int
     c->comm_world = world;
     LBM_CUDA(c, cudaMalloc(&c->token, 3 * sizeof(int)));
     LBM_CUDA(c, cudaMemset(c->token, 0, 3 * sizeof(int)));
+    if (c->sync_mode == LBM_SYNC_NONE) c->sync_mode = LBM_SYNC_NCCL;  // dense halos until lbm_comm_fused says otherwise
     return LBM_OK;
 }
 
-int lbm_comm_fused(lbm_ctx *c, int enable)
+int lbm_comm_fused(lbm_ctx *c, int mode)
 {
     if (!c) return LBM_ERR_INVALID;
-    if (!enable) {
-        c->fused = false;
-        return LBM_OK;
-    }
-    if (!c->comm) return fail(c, LBM_ERR_STATE, "lbm_comm_fused: no communicator (lbm_comm_init)");
     const bool has_lo = c->z_begin > 0, has_hi = c->z_end < c->dim;
-    if ((has_lo && !c->peer_f[0][0]) || (has_hi && !c->peer_f[1][0]))
-        return fail(c, LBM_ERR_STATE, "lbm_comm_fused: an interior face has no attached neighbour (lbm_ipc_attach)");
-    c->fused = has_lo || has_hi;
-    return LBM_OK;
+    const bool attached = (!has_lo || c->peer_f[0][0]) && (!has_hi || c->peer_f[1][0]);
+    switch (mode) {
+        case LBM_FUSED_OFF:
+            c->fused = false;
+            c->sync_mode = c->comm ? LBM_SYNC_NCCL : LBM_SYNC_NONE;
+            return LBM_OK;
+        case LBM_FUSED_FLAGS:
+            if (!attached)
+                return fail(c, LBM_ERR_STATE, "lbm_comm_fused: an interior face has no attached neighbour (lbm_ipc_attach)");
+            c->fused = has_lo || has_hi;
+            c->sync_mode = c->fused ? LBM_SYNC_FLAGS : LBM_SYNC_NONE;
+            c->initialised = false;  // the phase protocol starts with lbm_init on every rank
+            return LBM_OK;
+        case LBM_FUSED_TOKEN:
+            if (!c->comm) return fail(c, LBM_ERR_STATE, "lbm_comm_fused: the token form needs a communicator (lbm_comm_init)");
+            if (!attached)
+                return fail(c, LBM_ERR_STATE, "lbm_comm_fused: an interior face has no attached neighbour (lbm_ipc_attach)");
+            c->fused = has_lo || has_hi;
+            c->sync_mode = LBM_SYNC_NCCL;
+            return LBM_OK;
+        default: return fail(c, LBM_ERR_INVALID, "lbm_comm_fused: unknown mode %d", mode);
+    }
 }
 
 // ---- CUDA IPC: let a neighbouring PROCESS's boundary kernel store straight into this lattice ----
@@ -787,8 +704,30 @@ struct IpcBlob {
     cudaIpcMemHandle_t f[2];
     int32_t zs0, nz_local, dim, precision;
     int64_t stride, n_alloc;
+    int32_t z_begin, z_end;   // owned planes: the attaching side checks that the slabs are adjacent
+    int64_t flag_off;         // byte offset of the two incoming flag words behind lattice 0
 };
 static_assert(sizeof(IpcBlob) <= LBM_IPC_HANDLE_BYTES, "IpcBlob must fit LBM_IPC_HANDLE_BYTES");
+
+// geometry checks shared by lbm_ipc_attach and lbm_peer_attach
+int check_neighbour(lbm_ctx *c, int face, const char *who, int dim, int precision, int64_t stride, int zs0, int nz_local,
+                    int z_begin, int z_end)
+{
+    if (c->peer_f[face][0]) return fail(c, LBM_ERR_STATE, "%s: face %d already has a neighbour", who, face);
+    if ((face == 0 && c->z_begin == 0) || (face == 1 && c->z_end == c->dim))
+        return fail(c, LBM_ERR_INVALID, "%s: face %d lies on the cube boundary", who, face);
+    if (c->aa) return fail(c, LBM_ERR_INVALID, "%s: the AA variant is single-device", who);
+    if (dim != c->dim || precision != c->p.precision || stride != c->p.stride)
+        return fail(c, LBM_ERR_INVALID, "%s: the neighbour runs a different configuration", who);
+    // the slabs must be adjacent: my boundary plane is the neighbour's HALO plane, not one it owns
+    if ((face == 0 && z_end != c->z_begin) || (face == 1 && z_begin != c->z_end))
+        return fail(c, LBM_ERR_INVALID, "%s: the neighbour owns planes [%d, %d), not adjacent to face %d of [%d, %d)", who,
+                    z_begin, z_end, face, c->z_begin, c->z_end);
+    const int my_plane = face == 0 ? c->z_begin : c->z_end - 1;
+    if (my_plane < zs0 || my_plane >= zs0 + nz_local)
+        return fail(c, LBM_ERR_INVALID, "%s: the neighbour does not store plane %d", who, my_plane);
+    return LBM_OK;
+}
 }  // namespace
 
 int lbm_ipc_export(lbm_ctx *c, uint8_t out[LBM_IPC_HANDLE_BYTES])
@@ -805,6 +744,9 @@ int lbm_ipc_export(lbm_ctx *c, uint8_t out[LBM_IPC_HANDLE_BYTES])
     b.precision = c->p.precision;
     b.stride = c->p.stride;
     b.n_alloc = c->n_alloc;
+    b.z_begin = c->z_begin;
+    b.z_end = c->z_end;
+    b.flag_off = (int64_t)c->flag_off;
     std::memset(out, 0, LBM_IPC_HANDLE_BYTES);
     std::memcpy(out, &b, sizeof b);
     return LBM_OK;
@@ -813,19 +755,11 @@ int lbm_ipc_export(lbm_ctx *c, uint8_t out[LBM_IPC_HANDLE_BYTES])
 int lbm_ipc_attach(lbm_ctx *c, int face, const uint8_t in[LBM_IPC_HANDLE_BYTES])
 {
     if (!c || !in || (face != 0 && face != 1)) return LBM_ERR_INVALID;
-    if (c->peer_f[face][0]) return fail(c, LBM_ERR_STATE, "lbm_ipc_attach: face %d already has a neighbour", face);
-    if ((face == 0 && c->z_begin == 0) || (face == 1 && c->z_end == c->dim))
-        return fail(c, LBM_ERR_INVALID, "lbm_ipc_attach: face %d lies on the cube boundary", face);
     IpcBlob b;
     std::memcpy(&b, in, sizeof b);
-    if (b.dim != c->dim || b.precision != c->p.precision || b.stride != c->p.stride)
-        return fail(c, LBM_ERR_INVALID, "lbm_ipc_attach: the neighbour runs a different configuration");
-    // the neighbour must store the plane I write: its halo plane next to my boundary plane
-    const int my_plane = face == 0 ? c->z_begin : c->z_end - 1;
-    if (my_plane < b.zs0 || my_plane >= b.zs0 + b.nz_local)
-        return fail(c, LBM_ERR_INVALID, "lbm_ipc_attach: the neighbour does not store plane %d", my_plane);
-    int rc = use_device(c);
+    int rc = check_neighbour(c, face, "lbm_ipc_attach", b.dim, b.precision, b.stride, b.zs0, b.nz_local, b.z_begin, b.z_end);
     if (rc != LBM_OK) return rc;
+    if ((rc = use_device(c)) != LBM_OK) return rc;
     void *p[2] = {nullptr, nullptr};
     for (int i = 0; i < 2; ++i) {
         const cudaError_t e = cudaIpcOpenMemHandle(&p[i], b.f[i], cudaIpcMemLazyEnablePeerAccess);
@@ -838,7 +772,56 @@ int lbm_ipc_attach(lbm_ctx *c, int face, const uint8_t in[LBM_IPC_HANDLE_BYTES])
     c->peer_f[face][0] = p[0];
     c->peer_f[face][1] = p[1];
     c->peer_zs0[face] = b.zs0;
+    // I am the neighbour's high neighbour when it sits on my low face, and vice versa
+    c->peer_flag[face] = reinterpret_cast<unsigned *>(static_cast<char *>(p[0]) + b.flag_off) + (face == 0 ? 1 : 0);
     c->peer_ipc[face] = true;
+    return LBM_OK;
+}
+
+int lbm_peer_attach(lbm_ctx *c, int face, lbm_ctx *nb)
+{
+    if (!c || !nb || c == nb || (face != 0 && face != 1)) return LBM_ERR_INVALID;
+    int rc = check_neighbour(c, face, "lbm_peer_attach", nb->dim, nb->p.precision, nb->p.stride, nb->zs0, nb->nz_local,
+                             nb->z_begin, nb->z_end);
+    if (rc != LBM_OK) return rc;
+    if (nb->aa) return fail(c, LBM_ERR_INVALID, "lbm_peer_attach: the AA variant is single-device");
+    if (nb->device != c->device) {
+        int can = 0;
+        if ((rc = use_device(c)) != LBM_OK) return rc;
+        if (cudaDeviceCanAccessPeer(&can, c->device, nb->device) != cudaSuccess || !can)
+            return fail(c, LBM_ERR_CUDA, "lbm_peer_attach: device %d cannot access peer %d", c->device, nb->device);
+        const cudaError_t e = cudaDeviceEnablePeerAccess(nb->device, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+        else LBM_CUDA(c, e);
+    }
+    c->peer[face] = nb;
+    c->peer_f[face][0] = nb->f[0];
+    c->peer_f[face][1] = nb->f[1];
+    c->peer_zs0[face] = nb->zs0;
+    c->peer_flag[face] = reinterpret_cast<unsigned *>(static_cast<char *>(nb->f[0]) + nb->flag_off) + (face == 0 ? 1 : 0);
+    c->peer_ipc[face] = false;
+    return LBM_OK;
+}
+
+int lbm_ipc_detach(lbm_ctx *c)
+{
+    if (!c) return LBM_ERR_INVALID;
+    int rc = use_device(c);
+    if (rc != LBM_OK) return rc;
+    // nothing of mine may still be storing into the neighbours
+    LBM_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->bstream) LBM_CUDA(c, cudaStreamSynchronize(c->bstream));
+    for (int face = 0; face < 2; ++face) {
+        if (c->peer_ipc[face])
+            for (int i = 0; i < 2; ++i)
+                if (c->peer_f[face][i]) cudaIpcCloseMemHandle(c->peer_f[face][i]);
+        c->peer[face] = nullptr;
+        c->peer_f[face][0] = c->peer_f[face][1] = nullptr;
+        c->peer_flag[face] = nullptr;
+        c->peer_ipc[face] = false;
+    }
+    c->fused = false;
+    c->sync_mode = c->comm ? LBM_SYNC_NCCL : LBM_SYNC_NONE;
     return LBM_OK;
 }
 
@@ -869,17 +852,18 @@ void lbm_destroy(lbm_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     for (auto &e : c->compute_events) {
         if (e.start) cudaEventDestroy(e.start);
         if (e.stop) cudaEventDestroy(e.stop);
     }
+    if (c->bstream) cudaStreamSynchronize(c->bstream);
     for (int face = 0; face < 2; ++face)
         if (c->peer_ipc[face])
             for (int i = 0; i < 2; ++i)
                 if (c->peer_f[face][i]) cudaIpcCloseMemHandle(c->peer_f[face][i]);
     for (int i = 0; i < 2; ++i)
         if (c->graph_exec[i]) cudaGraphExecDestroy(c->graph_exec[i]);
-    if (c->bstream) cudaStreamSynchronize(c->bstream);
     if (c->comm) lbm_nccl_destroy(c->comm);
     for (int i = 0; i < 2; ++i) {
         if (c->ev_bk[i]) cudaEventDestroy(c->ev_bk[i]);
@@ -887,8 +871,12 @@ void lbm_destroy(lbm_ctx *c)
     }
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->bstream) cudaStreamDestroy(c->bstream);
+    if (c->ev_copy_ready) cudaEventDestroy(c->ev_copy_ready);
+    if (c->ev_copy_done) cudaEventDestroy(c->ev_copy_done);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->ev_init_start) cudaEventDestroy(c->ev_init_start);
     if (c->ev_last) cudaEventDestroy(c->ev_last);
+    lbm_nvrtc_destroy(c);
     for (int i = 0; i < 2; ++i) {
         if (c->f[i]) cudaFree(c->f[i]);
         if (c->halo_send[i]) cudaFree(c->halo_send[i]);
@@ -897,6 +885,7 @@ void lbm_destroy(lbm_ctx *c)
     if (c->rho) cudaFree(c->rho);
     if (c->u) cudaFree(c->u);
     if (c->tma_error) cudaFree(c->tma_error);
+    if (c->sync_local) cudaFree(c->sync_local);
     if (c->token) cudaFree(c->token);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
@@ -927,7 +916,7 @@ int lbm_create(const lbm_params *p, lbm_ctx **out)
         return fail(nullptr, LBM_ERR_INVALID, "lbm_create: bad z range [%d, %d)", zb, ze);
     switch (p->variant) {
         case LBM_VARIANT_AUTO: case LBM_VARIANT_SCALAR: case LBM_VARIANT_VEC2: case LBM_VARIANT_VEC4: break;
-        case LBM_VARIANT_TMA: break;
+        case LBM_VARIANT_TMA: case LBM_VARIANT_NVRTC: break;
         case LBM_VARIANT_AA:
             if (zb != 0 || ze != p->dim)
                 return fail(nullptr, LBM_ERR_INVALID, "lbm_create: the AA variant needs the whole cube on one device");
@@ -976,9 +965,11 @@ int lbm_create(const lbm_params *p, lbm_ctx **out)
     c->lay.smod = p->stride - 1;
     c->n_alloc = ((c->n_local + p->stride - 1) / p->stride) * p->stride;
     c->esize = p->precision == LBM_F32 ? 4 : 8;
-    if (p->stride <= p->dim) c->layout_mode = LM_ROWS;
-    else if (p->stride >= c->n_alloc) c->layout_mode = LM_SOA;
-    else c->layout_mode = LM_GENERIC;
+    // every stride is a power of two, so exactly one of the three uniform-offset modes applies
+    if (p->stride <= p->dim) c->layout_natural = LM_ROWS;
+    else if (p->stride >= c->n_alloc) c->layout_natural = LM_SOA;
+    else c->layout_natural = LM_BLOCKROWS;
+    c->layout_mode = c->layout_natural;
     if (p->reserved[0] == 1) c->layout_mode = LM_GENERIC;  // test hook: force the generic addressing
 
     // AUTO = one cell per thread.  Measured on B200 (profiles/): with 40-48 registers the scalar kernel
@@ -987,11 +978,9 @@ int lbm_create(const lbm_params *p, lbm_ctx **out)
     // shuffle) need 64-150 registers, drop to 16-24 warps per SM and are 3-8 % slower.  They stay
     // selectable.  Vector width is limited to 16-byte accesses inside one CSoA run.
     const int vmax = p->precision == LBM_F32 ? 4 : 2;
-    int vec = (p->variant == LBM_VARIANT_AUTO || p->variant == LBM_VARIANT_SCALAR) ? 1 : p->variant;
+    int vec = (p->variant == LBM_VARIANT_VEC2 || p->variant == LBM_VARIANT_VEC4) ? p->variant : 1;
     c->aa = p->variant == LBM_VARIANT_AA;
-    if (c->aa) vec = 1;
     if (p->variant == LBM_VARIANT_TMA) {
-        vec = 1;
         // eligibility; otherwise the scalar kernel is used
         c->tma = p->stride <= p->dim && p->stride * (long long)(p->precision == LBM_F32 ? 4 : 8) >= 16 && p->dim >= 32;
     }
@@ -999,6 +988,11 @@ int lbm_create(const lbm_params *p, lbm_ctx **out)
     while (vec > 1 && (p->stride % vec != 0 || p->dim % vec != 0)) vec /= 2;
     c->vec = vec;
     choose_block(c);
+
+    if (const char *t = std::getenv("LBM_SYNC_TIMEOUT_S")) {
+        const double s = std::atof(t);
+        if (s > 0) c->sync_timeout_ns = (unsigned long long)(s * 1e9);
+    }
 
     double eff[3];
     c->cf = make_consts<float>(p->viscosity, p->velocity, eff);
@@ -1018,23 +1012,27 @@ int lbm_create(const lbm_params *p, lbm_ctx **out)
     if (cuda_or_bail(cudaEventCreate(&c->ev_init_start), "cudaEventCreate")) return bail(LBM_ERR_CUDA);
     if (cuda_or_bail(cudaEventCreate(&c->ev_last), "cudaEventCreate")) return bail(LBM_ERR_CUDA);
 
-    const size_t f_bytes = (size_t)c->n_alloc * Q * c->esize;
+    c->f_bytes = (size_t)c->n_alloc * Q * c->esize;
+    c->flag_off = (c->f_bytes + 255) / 256 * 256;  // lattice 0 carries the slab flag words behind it (one IPC handle)
     const size_t m_bytes = (size_t)c->n_local * c->esize;
     for (int i = 0; i < (c->aa ? 1 : 2); ++i) {
-        cudaError_t err = cudaMalloc(&c->f[i], f_bytes);
+        const size_t bytes = i == 0 ? c->flag_off + 256 : c->f_bytes;
+        cudaError_t err = cudaMalloc(&c->f[i], bytes);
         if (err == cudaErrorMemoryAllocation) {
             cudaGetLastError();
             fail(c, LBM_ERR_OOM,
                  "lbm_create: cudaMalloc of lattice %d (%.1f GB) failed - cudaErrorMemoryAllocation; %s", i,
-                 (double)f_bytes / 1e9,
+                 (double)c->f_bytes / 1e9,
                  c->aa ? "split the cube over more GPUs"
                        : "the in-place variant (-A, LBM_VARIANT_AA) needs one lattice instead of two, or split the "
                          "cube over more GPUs (-G N)");
             return bail(LBM_ERR_OOM);
         }
         if (cuda_or_bail(err, "cudaMalloc(f)")) return bail(LBM_ERR_CUDA);
-        c->device_bytes += (int64_t)f_bytes;
+        c->device_bytes += (int64_t)c->f_bytes;
     }
+    // the flag words start at zero and are never reset: phases only grow (see run_slab_flags)
+    if (cuda_or_bail(cudaMemset(static_cast<char *>(c->f[0]) + c->flag_off, 0, 256), "cudaMemset(flags)")) return bail(LBM_ERR_CUDA);
     {
         cudaError_t err = cudaMalloc(&c->rho, m_bytes);
         if (cuda_or_bail(err, "cudaMalloc(rho)")) return bail(err == cudaErrorMemoryAllocation ? LBM_ERR_OOM : LBM_ERR_CUDA);
@@ -1050,6 +1048,10 @@ int lbm_create(const lbm_params *p, lbm_ctx **out)
         if (cuda_or_bail(cudaMalloc(&c->halo_recv[fidx], h_bytes), "cudaMalloc(halo)")) return bail(LBM_ERR_OOM);
         c->device_bytes += (int64_t)(2 * h_bytes);
     }
+    if (has_face[0] || has_face[1]) {
+        if (cuda_or_bail(cudaMalloc(&c->sync_local, 4 * sizeof(unsigned)), "cudaMalloc(sync)")) return bail(LBM_ERR_OOM);
+        if (cuda_or_bail(cudaMemset(c->sync_local, 0, 4 * sizeof(unsigned)), "cudaMemset(sync)")) return bail(LBM_ERR_CUDA);
+    }
 
     if (p->precision == LBM_F32) rc = compute_stale<float>(c, c->cf, c->stale_f);
     else rc = compute_stale<double>(c, c->cd, c->stale_d);
@@ -1057,6 +1059,10 @@ int lbm_create(const lbm_params *p, lbm_ctx **out)
 
     if (c->tma) {
         rc = setup_tma(c, prop.multiProcessorCount);
+        if (rc != LBM_OK) return bail(rc);
+    }
+    if (p->variant == LBM_VARIANT_NVRTC) {
+        rc = lbm_nvrtc_build(c);
         if (rc != LBM_OK) return bail(rc);
     }
 
@@ -1078,8 +1084,19 @@ int lbm_init(lbm_ctx *c)
     c->kernels_ms_accum = 0.0;
     c->launch_ms.clear();
     LBM_CUDA(c, cudaEventRecord(c->ev_init_start, c->stream));
-    if (c->p.precision == LBM_F32) LBM_CUDA(c, launch_init_t<float>(c, c->cf, c->stream));
-    else LBM_CUDA(c, launch_init_t<double>(c, c->cd, c->stream));
+    if (c->copy_pending) LBM_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copy_done, 0));  // `initialize` rewrites rho / u
+    if (c->sync_mode == LBM_SYNC_FLAGS) {
+        // `initialize` is a phase of its own: it rewrites my halo planes, so the neighbours' last stores
+        // into them (their previous phase) must have landed; afterwards they may store again
+        const bool has_lo = c->z_begin > 0, has_hi = c->z_end < c->dim;
+        c->phase += 1;
+        const SlabSync y = make_sync(c, c->phase - 1, c->phase);
+        LBM_CUDA(c, launch_slab_wait(y, has_lo, has_hi, c->stream));
+        LBM_CUDA(c, launch_init(c, c->stream));
+        LBM_CUDA(c, launch_slab_signal(y, has_lo, has_hi, c->stream));
+    } else {
+        LBM_CUDA(c, launch_init(c, c->stream));
+    }
     c->cur = 0;
     c->iteration = 0;
     c->launches = 0;
@@ -1101,95 +1118,122 @@ static int push_pair(lbm_ctx *c, EventPair *out)
 }
 
 // Fold finished event pairs into the accumulator so that very long runs driven by lbm_step do not
-// hold an unbounded number of CUDA events.
+// hold an unbounded number of CUDA events.  Entries are removed as they are folded; a pair whose stop
+// event was never recorded (an enqueue failed half way) is dropped without being measured.
 static int fold_events(lbm_ctx *c, bool all)
 {
     if (!all && c->compute_events.size() < 4096) return LBM_OK;
-    if (!c->compute_events.empty()) LBM_CUDA(c, cudaEventSynchronize(c->compute_events.back().stop));
-    for (auto &e : c->compute_events) {
-        float ms = 0.f;
-        LBM_CUDA(c, cudaEventElapsedTime(&ms, e.start, e.stop));
-        c->kernels_ms_accum += ms;
-        if (c->launch_ms.size() < (1u << 20)) c->launch_ms.push_back(ms);
+    int rc = LBM_OK;
+    while (!c->compute_events.empty()) {
+        EventPair e = c->compute_events.front();
+        c->compute_events.erase(c->compute_events.begin());
+        if (e.stop_recorded && rc == LBM_OK) {
+            float ms = 0.f;
+            cudaError_t err = cudaEventSynchronize(e.stop);
+            if (err == cudaSuccess) err = cudaEventElapsedTime(&ms, e.start, e.stop);
+            if (err == cudaSuccess) {
+                c->kernels_ms_accum += ms;
+                if (c->launch_ms.size() < (1u << 20)) c->launch_ms.push_back(ms);
+            } else {
+                rc = fail(c, LBM_ERR_CUDA, "fold_events: %s(%d)", cudaGetErrorName(err), (int)err);
+            }
+        }
         cudaEventDestroy(e.start);
         cudaEventDestroy(e.stop);
     }
-    c->compute_events.clear();
+    return rc;
+}
+
+// Opens a timed batch on the main stream; close_batch() records its end.  A batch that is never closed
+// (an error in between) is discarded by fold_events.
+static int open_batch(lbm_ctx *c)
+{
+    int rc = fold_events(c, false);
+    if (rc != LBM_OK) return rc;
+    EventPair ep;
+    if ((rc = push_pair(c, &ep)) != LBM_OK) return rc;
+    const cudaError_t e = cudaEventRecord(ep.start, c->stream);
+    if (e != cudaSuccess) {
+        cudaEventDestroy(ep.start);
+        cudaEventDestroy(ep.stop);
+        return fail(c, LBM_ERR_CUDA, "cudaEventRecord(%d) - %s", (int)e, cudaGetErrorName(e));
+    }
+    c->compute_events.push_back(ep);
+    return LBM_OK;
+}
+static int close_batch(lbm_ctx *c)
+{
+    LBM_CUDA(c, cudaEventRecord(c->compute_events.back().stop, c->stream));
+    c->compute_events.back().stop_recorded = true;
+    return record_last(c);
+}
+
+// n iterations of whatever schedule the context is in; iteration numbers continue from the counter
+static int run_iterations(lbm_ctx *c, int n_iterations, int every, bool allow_graphs)
+{
+    if (c->sync_mode == LBM_SYNC_FLAGS) return run_slab_flags(c, n_iterations, every);
+    if (c->sync_mode == LBM_SYNC_NCCL) return run_slab_with_comm(c, n_iterations, every);
+    int left = n_iterations;
+    while (left > 0) {
+        const int64_t it = c->iteration + 1;  // 1-based like lbmcl.hpp:435
+        // launch-bound lattices: replay a captured chunk of unflagged iterations as one graph
+        // (capturing + instantiating a chunk costs a few hundred microseconds of host time: only
+        // worth it when at least LBM_GRAPH_MIN_CHUNKS replays follow, or when the graph exists already)
+        const int gpar = c->aa ? (int)(c->iteration & 1) : c->cur;
+        const bool have_graph = c->graph_exec[gpar] != nullptr && c->graph_stream == c->stream;
+        if (allow_graphs && c->dim <= LBM_GRAPH_MAX_DIM && left >= LBM_GRAPH_CHUNK &&
+            (have_graph || left >= LBM_GRAPH_MIN_CHUNKS * LBM_GRAPH_CHUNK)) {
+            const int64_t last = it + LBM_GRAPH_CHUNK - 1;
+            const bool flagged = every != 0 && (last / every) != ((it - 1) / every);
+            if (!flagged) {
+                const int rc = launch_graph_chunk(c);
+                if (rc != LBM_OK) return rc;
+                left -= LBM_GRAPH_CHUNK;
+                continue;
+            }
+        }
+        const bool macro = every != 0 && (it % every) == 0;
+        LBM_CUDA(c, launch_step(c, Planes::range(c->z_begin, c->z_end), macro, PEER_NONE, c->stream));
+        c->cur ^= 1;
+        c->iteration = it;
+        --left;
+    }
+    return LBM_OK;
+}
+
+// a slab whose neighbours are attached but that has no schedule of its own is driven by lbm_group_run
+static int check_drivable(lbm_ctx *c, const char *who)
+{
+    if (!c->initialised) return fail(c, LBM_ERR_STATE, "%s before lbm_init", who);
+    if (c->sync_mode == LBM_SYNC_NONE && has_neighbours(c))
+        return fail(c, LBM_ERR_STATE, "%s: this slab has peer neighbours; drive it through lbm_group_run (same "
+                                      "process), or enable a transport (lbm_comm_fused / lbm_comm_init)", who);
     return LBM_OK;
 }
 
 int lbm_step(lbm_ctx *c, int update_macro)
 {
     if (!c) return LBM_ERR_INVALID;
-    if (!c->initialised) return fail(c, LBM_ERR_STATE, "lbm_step before lbm_init");
-    int rc = use_device(c);
+    int rc = check_drivable(c, "lbm_step");
     if (rc != LBM_OK) return rc;
-    if ((rc = fold_events(c, false)) != LBM_OK) return rc;
-    EventPair ep;
-    if ((rc = push_pair(c, &ep)) != LBM_OK) return rc;
-    c->compute_events.push_back(ep);
-    LBM_CUDA(c, cudaEventRecord(ep.start, c->stream));
-    if (c->comm) {
-        // a slab with a communicator always goes through the exchange schedule (one iteration of it)
-        if ((rc = run_slab_with_comm(c, 1, update_macro ? 1 : 0)) != LBM_OK) return rc;
-    } else {
-        if (c->peer_f[0][0] || c->peer_f[1][0])
-            return fail(c, LBM_ERR_STATE, "lbm_step: this slab has peer neighbours; drive it through lbm_group_run");
-        LBM_CUDA(c, launch_step(c, c->z_begin, c->z_end, update_macro != 0, c->stream));
-        c->cur ^= 1;
-        c->iteration += 1;
-    }
-    LBM_CUDA(c, cudaEventRecord(ep.stop, c->stream));
-    return record_last(c);
+    if ((rc = use_device(c)) != LBM_OK) return rc;
+    if ((rc = open_batch(c)) != LBM_OK) return rc;
+    // one reference `compute` launch: never a graph replay
+    if ((rc = run_iterations(c, 1, update_macro ? 1 : 0, false)) != LBM_OK) return rc;
+    return close_batch(c);
 }
 
 int lbm_run(lbm_ctx *c, int n_iterations, int every)
 {
     if (!c) return LBM_ERR_INVALID;
-    if (!c->initialised) return fail(c, LBM_ERR_STATE, "lbm_run before lbm_init");
     if (n_iterations < 0 || every < 0) return fail(c, LBM_ERR_INVALID, "lbm_run: negative argument");
-    if (n_iterations == 0) return LBM_OK;
-    if (!c->comm && (c->peer_f[0][0] || c->peer_f[1][0]))
-        return fail(c, LBM_ERR_STATE, "lbm_run: this slab has peer neighbours; drive it through lbm_group_run "
-                                      "(same process) or give it a communicator (lbm_comm_init)");
-    int rc = use_device(c);
+    int rc = check_drivable(c, "lbm_run");
     if (rc != LBM_OK) return rc;
-    if ((rc = fold_events(c, false)) != LBM_OK) return rc;
-    EventPair ep;
-    if ((rc = push_pair(c, &ep)) != LBM_OK) return rc;
-    c->compute_events.push_back(ep);
-    LBM_CUDA(c, cudaEventRecord(ep.start, c->stream));
-    if (c->comm) {
-        if ((rc = run_slab_with_comm(c, n_iterations, every)) != LBM_OK) return rc;
-    } else {
-        int left = n_iterations;
-        while (left > 0) {
-            const int64_t it = c->iteration + 1;  // 1-based like lbmcl.hpp:435
-            // launch-bound lattices: replay a captured chunk of unflagged iterations as one graph
-            // (capturing + instantiating a chunk costs a few hundred microseconds of host time: only
-            // worth it when at least LBM_GRAPH_MIN_CHUNKS replays follow, or when the graph exists already)
-            const int gpar = c->aa ? (int)(c->iteration & 1) : c->cur;
-            const bool have_graph = c->graph_exec[gpar] != nullptr && c->graph_stream == c->stream;
-            if (c->dim <= LBM_GRAPH_MAX_DIM && left >= LBM_GRAPH_CHUNK &&
-                (have_graph || left >= LBM_GRAPH_MIN_CHUNKS * LBM_GRAPH_CHUNK) && c->peer_f[0][0] == nullptr &&
-                c->peer_f[1][0] == nullptr) {
-                const int64_t last = it + LBM_GRAPH_CHUNK - 1;
-                const bool flagged = every != 0 && (last / every) != ((it - 1) / every);
-                if (!flagged) {
-                    if ((rc = launch_graph_chunk(c)) != LBM_OK) return rc;
-                    left -= LBM_GRAPH_CHUNK;
-                    continue;
-                }
-            }
-            const bool macro = every != 0 && (it % every) == 0;
-            LBM_CUDA(c, launch_step(c, c->z_begin, c->z_end, macro, c->stream));
-            c->cur ^= 1;
-            c->iteration = it;
-            --left;
-        }
-    }
-    LBM_CUDA(c, cudaEventRecord(ep.stop, c->stream));
-    return record_last(c);
+    if (n_iterations == 0) return LBM_OK;
+    if ((rc = use_device(c)) != LBM_OK) return rc;
+    if ((rc = open_batch(c)) != LBM_OK) return rc;
+    if ((rc = run_iterations(c, n_iterations, every, true)) != LBM_OK) return rc;
+    return close_batch(c);
 }
 
 int lbm_sync(lbm_ctx *c)
@@ -1203,52 +1247,108 @@ int lbm_sync(lbm_ctx *c)
         LBM_CUDA(c, cudaMemcpy(&flag, c->tma_error, sizeof(int), cudaMemcpyDeviceToHost));
         if (flag) return fail(c, LBM_ERR_CUDA, "TMA variant: an mbarrier wait timed out (bulk copy never completed)");
     }
+    if (c->sync_mode == LBM_SYNC_FLAGS && c->sync_local) {
+        unsigned flag = 0;
+        LBM_CUDA(c, cudaMemcpy(&flag, c->sync_local + 2, sizeof flag, cudaMemcpyDeviceToHost));
+        if (flag)
+            return fail(c, LBM_ERR_CUDA, "z-slab transport: a wait for a neighbour's phase flag timed out after %.0f s "
+                                         "(a rank died or the ranks ran different schedules); results are invalid",
+                        (double)c->sync_timeout_ns * 1e-9);
+    }
+    return LBM_OK;
+}
+
+// device -> host copies of rho / u on stream `s`; slab == false: global layouts, owned planes only
+static int enqueue_macro_copies(lbm_ctx *c, void *rho_host, void *u_host, bool slab, cudaStream_t s)
+{
+    const long long plane = (long long)c->dim * c->dim;
+    const long long n_cube = plane * c->dim;
+    const size_t off_local = (size_t)(c->z_begin - c->zs0) * plane * c->esize;
+    const size_t off_host = slab ? 0 : (size_t)c->z_begin * plane * c->esize;
+    const size_t bytes = (size_t)(c->z_end - c->z_begin) * plane * c->esize;
+    const size_t u_pitch = slab ? bytes : (size_t)n_cube * c->esize;
+    if (rho_host)
+        LBM_CUDA(c, cudaMemcpyAsync((char *)rho_host + off_host, (const char *)c->rho + off_local, bytes,
+                                    cudaMemcpyDeviceToHost, s));
+    if (u_host)
+        for (int k = 0; k < 3; ++k)
+            LBM_CUDA(c, cudaMemcpyAsync((char *)u_host + (size_t)k * u_pitch + off_host,
+                                        (const char *)c->u + (size_t)k * c->n_local * c->esize + off_local, bytes,
+                                        cudaMemcpyDeviceToHost, s));
+    return LBM_OK;
+}
+
+static int read_macros_blocking(lbm_ctx *c, void *rho_host, void *u_host, bool slab, const char *who)
+{
+    if (!c) return LBM_ERR_INVALID;
+    if (!c->initialised) return fail(c, LBM_ERR_STATE, "%s before lbm_init", who);
+    int rc = use_device(c);
+    if (rc != LBM_OK) return rc;
+    if ((rc = enqueue_macro_copies(c, rho_host, u_host, slab, c->stream)) != LBM_OK) return rc;
+    if ((rc = record_last(c)) != LBM_OK) return rc;
+    LBM_CUDA(c, cudaStreamSynchronize(c->stream));
     return LBM_OK;
 }
 
 int lbm_read_macros(lbm_ctx *c, void *rho_host, void *u_host)
 {
-    if (!c) return LBM_ERR_INVALID;
-    if (!c->initialised) return fail(c, LBM_ERR_STATE, "lbm_read_macros before lbm_init");
-    int rc = use_device(c);
-    if (rc != LBM_OK) return rc;
-    const long long plane = (long long)c->dim * c->dim;
-    const long long n_cube = plane * c->dim;
-    const size_t off_local = (size_t)(c->z_begin - c->zs0) * plane * c->esize;
-    const size_t off_global = (size_t)c->z_begin * plane * c->esize;
-    const size_t bytes = (size_t)(c->z_end - c->z_begin) * plane * c->esize;
-    if (rho_host)
-        LBM_CUDA(c, cudaMemcpyAsync((char *)rho_host + off_global, (const char *)c->rho + off_local, bytes,
-                                    cudaMemcpyDeviceToHost, c->stream));
-    if (u_host)
-        for (int k = 0; k < 3; ++k)
-            LBM_CUDA(c, cudaMemcpyAsync((char *)u_host + (size_t)k * n_cube * c->esize + off_global,
-                                        (const char *)c->u + (size_t)k * c->n_local * c->esize + off_local, bytes,
-                                        cudaMemcpyDeviceToHost, c->stream));
-    if ((rc = record_last(c)) != LBM_OK) return rc;
-    LBM_CUDA(c, cudaStreamSynchronize(c->stream));
-    return LBM_OK;
+    return read_macros_blocking(c, rho_host, u_host, false, "lbm_read_macros");
 }
 
 int lbm_read_macros_slab(lbm_ctx *c, void *rho_slab, void *u_slab)
 {
+    return read_macros_blocking(c, rho_slab, u_slab, true, "lbm_read_macros_slab");
+}
+
+// ---- asynchronous read-back ----
+
+int lbm_host_alloc(size_t bytes, void **out)
+{
+    if (!out) return LBM_ERR_INVALID;
+    *out = nullptr;
+    const cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(nullptr, LBM_ERR_OOM, "lbm_host_alloc: cudaHostAlloc(%zu) - %s", bytes, cudaGetErrorName(e));
+    }
+    return LBM_OK;
+}
+
+void lbm_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+int lbm_read_macros_async(lbm_ctx *c, void *rho_host, void *u_host)
+{
     if (!c) return LBM_ERR_INVALID;
-    if (!c->initialised) return fail(c, LBM_ERR_STATE, "lbm_read_macros_slab before lbm_init");
+    if (!c->initialised) return fail(c, LBM_ERR_STATE, "lbm_read_macros_async before lbm_init");
     int rc = use_device(c);
     if (rc != LBM_OK) return rc;
-    const long long plane = (long long)c->dim * c->dim;
-    const size_t off_local = (size_t)(c->z_begin - c->zs0) * plane * c->esize;
-    const size_t bytes = (size_t)(c->z_end - c->z_begin) * plane * c->esize;
-    if (rho_slab)
-        LBM_CUDA(c, cudaMemcpyAsync(rho_slab, (const char *)c->rho + off_local, bytes, cudaMemcpyDeviceToHost, c->stream));
-    if (u_slab)
-        for (int k = 0; k < 3; ++k)
-            LBM_CUDA(c, cudaMemcpyAsync((char *)u_slab + (size_t)k * bytes,
-                                        (const char *)c->u + (size_t)k * c->n_local * c->esize + off_local, bytes,
-                                        cudaMemcpyDeviceToHost, c->stream));
-    if ((rc = record_last(c)) != LBM_OK) return rc;
-    LBM_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (!c->copy_stream) {
+        LBM_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        LBM_CUDA(c, cudaEventCreateWithFlags(&c->ev_copy_ready, cudaEventDisableTiming));
+        LBM_CUDA(c, cudaEventCreate(&c->ev_copy_done));
+    }
+    // the copy sees everything enqueued so far and nothing later; later kernels that overwrite rho / u
+    // wait for ev_copy_done (launch_step_p), everything else runs alongside the copy
+    LBM_CUDA(c, cudaEventRecord(c->ev_copy_ready, c->stream));
+    LBM_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_copy_ready, 0));
+    if ((rc = enqueue_macro_copies(c, rho_host, u_host, false, c->copy_stream)) != LBM_OK) return rc;
+    LBM_CUDA(c, cudaEventRecord(c->ev_copy_done, c->copy_stream));
+    c->copy_pending = true;
     return LBM_OK;
+}
+
+int lbm_read_wait(lbm_ctx *c)
+{
+    if (!c) return LBM_ERR_INVALID;
+    if (!c->copy_pending) return LBM_OK;
+    int rc = use_device(c);
+    if (rc != LBM_OK) return rc;
+    LBM_CUDA(c, cudaEventSynchronize(c->ev_copy_done));
+    c->copy_pending = false;
+    return record_last(c);  // "Total time" covers the read-back like the reference's blocking reads do (lbmcl.hpp:548-556)
 }
 
 int lbm_read_map(lbm_ctx *c, int32_t *map_host)
@@ -1259,10 +1359,7 @@ int lbm_read_map(lbm_ctx *c, int32_t *map_host)
     const long long n_cube = (long long)c->dim * c->dim * c->dim;
     int *d = nullptr;
     LBM_CUDA(c, cudaMalloc(&d, (size_t)n_cube * sizeof(int)));
-    const int bx = c->dim < 64 ? c->dim : 64;
-    const int by = (256 / bx) < c->dim ? (256 / bx) : c->dim;
-    map_kernel<<<dim3(c->dim / bx, c->dim / by, c->dim), dim3(bx, by, 1), 0, c->stream>>>(d, c->dim);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launch_map(d, c->dim, c->stream);
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(map_host, d, (size_t)n_cube * sizeof(int), cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
@@ -1271,38 +1368,39 @@ int lbm_read_map(lbm_ctx *c, int32_t *map_host)
     return record_last(c);
 }
 
+// The reference's view of the lattice the next iteration reads, over the context's OWNED planes, written
+// into the device buffer `d` of 19 * DIM^3 elements in the reference's global CSoA order.
+static cudaError_t enqueue_reference_view(lbm_ctx *c, void *d)
+{
+    ViewCfg v{};
+    v.dim = c->dim;
+    v.zs0 = c->zs0;
+    v.nz_local = c->nz_local;
+    v.z_begin = c->z_begin;
+    v.z_end = c->z_end;
+    v.lay_local = c->lay;
+    v.lay_global = c->lay;
+    v.pristine = c->iteration == 0 ? 1 : 0;
+    v.aa_swapped = (c->iteration % 2) == 1 ? 1 : 0;
+    const void *src = c->aa ? c->f[0] : c->f[c->cur];
+    if (c->p.precision == LBM_F32)
+        return launch_view_f32((const float *)src, (float *)d, v, c->cf, c->aa, c->stream);
+    return launch_view_f64((const double *)src, (double *)d, v, c->cd, c->aa, c->stream);
+}
+
 int lbm_read_f(lbm_ctx *c, void *f_host)
 {
     if (!c || !f_host) return LBM_ERR_INVALID;
     if (!c->initialised) return fail(c, LBM_ERR_STATE, "lbm_read_f before lbm_init");
     if (c->z_begin != 0 || c->z_end != c->dim)
-        return fail(c, LBM_ERR_INVALID, "lbm_read_f: only on a context that owns the whole cube");
+        return fail(c, LBM_ERR_INVALID, "lbm_read_f: only on a context that owns the whole cube (slabs: lbm_group_read_f)");
     int rc = use_device(c);
     if (rc != LBM_OK) return rc;
     const long long n_cube = (long long)c->dim * c->dim * c->dim;
     const size_t bytes = (size_t)n_cube * Q * c->esize;
     void *d = nullptr;
     LBM_CUDA(c, cudaMalloc(&d, bytes));
-    const int bx = c->dim < 64 ? c->dim : 64;
-    const int by = (256 / bx) < c->dim ? (256 / bx) : c->dim;
-    const dim3 b(bx, by, 1), g(c->dim / bx, c->dim / by, c->dim);
-    const int pristine = c->iteration == 0 ? 1 : 0;
-    if (c->aa) {
-        const int swapped = (c->iteration % 2) == 1 ? 1 : 0;
-        if (c->p.precision == LBM_F32)
-            reference_view_aa_kernel<float><<<g, b, 0, c->stream>>>((const float *)c->f[0], (float *)d, c->dim, c->lay,
-                                                                    c->cf, swapped, pristine);
-        else
-            reference_view_aa_kernel<double><<<g, b, 0, c->stream>>>((const double *)c->f[0], (double *)d, c->dim,
-                                                                     c->lay, c->cd, swapped, pristine);
-    } else if (c->p.precision == LBM_F32)
-        reference_view_kernel<float><<<g, b, 0, c->stream>>>((const float *)c->f[c->cur], (float *)d, c->dim, c->zs0,
-                                                             c->nz_local, 0, c->dim, c->lay, c->lay, c->cf, pristine);
-    else
-        reference_view_kernel<double><<<g, b, 0, c->stream>>>((const double *)c->f[c->cur], (double *)d, c->dim,
-                                                              c->zs0, c->nz_local, 0, c->dim, c->lay, c->lay, c->cd,
-                                                              pristine);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = enqueue_reference_view(c, d);
     if (e == cudaSuccess) e = cudaMemcpyAsync(f_host, d, bytes, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     cudaFree(d);
@@ -1388,12 +1486,14 @@ int lbm_step_planes(lbm_ctx *c, int z_begin, int z_end, int update_macro)
     if (!c) return LBM_ERR_INVALID;
     if (!c->initialised) return fail(c, LBM_ERR_STATE, "lbm_step_planes before lbm_init");
     if (c->aa) return fail(c, LBM_ERR_INVALID, "lbm_step_planes: not available with the AA variant");
+    if (c->sync_mode == LBM_SYNC_FLAGS)
+        return fail(c, LBM_ERR_STATE, "lbm_step_planes: the flag transport drives whole iterations (lbm_run / lbm_step)");
     if (z_begin < c->z_begin || z_end > c->z_end || z_begin > z_end)
         return fail(c, LBM_ERR_INVALID, "lbm_step_planes: [%d, %d) outside the owned planes [%d, %d)", z_begin,
                     z_end, c->z_begin, c->z_end);
     int rc = use_device(c);
     if (rc != LBM_OK) return rc;
-    LBM_CUDA(c, launch_step(c, z_begin, z_end, update_macro != 0, c->stream));
+    LBM_CUDA(c, launch_step(c, Planes::range(z_begin, z_end), update_macro != 0, PEER_NONE, c->stream));
     return LBM_OK;
 }
 
@@ -1420,19 +1520,13 @@ int64_t lbm_halo_elems(const lbm_ctx *c) { return c ? (int64_t)5 * c->dim * c->d
 void *lbm_halo_send_buffer(lbm_ctx *c, int face) { return (c && (face == 0 || face == 1)) ? c->halo_send[face] : nullptr; }
 void *lbm_halo_recv_buffer(lbm_ctx *c, int face) { return (c && (face == 0 || face == 1)) ? c->halo_recv[face] : nullptr; }
 
-}  // extern "C"
-
-template <typename T, bool PACK>
-static cudaError_t halo_launch(lbm_ctx *c, void *lattice, void *dense, long long plane_local, int dir_up)
+static cudaError_t halo_launch(lbm_ctx *c, void *lattice, void *dense, long long plane_local, int dir_up, bool pack)
 {
-    const int bx = c->dim < 256 ? c->dim : 256;
-    const dim3 b(bx, 1, 1), g(c->dim / bx, c->dim, 5);
-    halo_kernel<T, PACK><<<g, b, 0, c->stream>>>((T *)lattice, (T *)dense, c->dim, plane_local, c->lay, dir_up);
     c->launches += 1;
-    return cudaGetLastError();
+    if (c->p.precision == LBM_F32)
+        return launch_halo_f32((float *)lattice, (float *)dense, c->dim, plane_local, c->lay, dir_up, pack, c->stream);
+    return launch_halo_f64((double *)lattice, (double *)dense, c->dim, plane_local, c->lay, dir_up, pack, c->stream);
 }
-
-extern "C" {
 
 // Packs, from the lattice the NEXT iteration reads (i.e. the one just written), what the neighbours
 // will gather: low face -> populations with e_z = -1 of plane z_begin; high face -> e_z = +1 of plane
@@ -1443,17 +1537,8 @@ int lbm_halo_pack(lbm_ctx *c)
     int rc = use_device(c);
     if (rc != LBM_OK) return rc;
     void *lat = c->f[c->cur];
-    const bool f32 = c->p.precision == LBM_F32;
-    if (c->halo_send[0]) {
-        const long long pl = c->z_begin - c->zs0;
-        LBM_CUDA(c, f32 ? halo_launch<float, true>(c, lat, c->halo_send[0], pl, 0)
-                        : halo_launch<double, true>(c, lat, c->halo_send[0], pl, 0));
-    }
-    if (c->halo_send[1]) {
-        const long long pl = (c->z_end - 1) - c->zs0;
-        LBM_CUDA(c, f32 ? halo_launch<float, true>(c, lat, c->halo_send[1], pl, 1)
-                        : halo_launch<double, true>(c, lat, c->halo_send[1], pl, 1));
-    }
+    if (c->halo_send[0]) LBM_CUDA(c, halo_launch(c, lat, c->halo_send[0], c->z_begin - c->zs0, 0, true));
+    if (c->halo_send[1]) LBM_CUDA(c, halo_launch(c, lat, c->halo_send[1], (c->z_end - 1) - c->zs0, 1, true));
     return LBM_OK;
 }
 
@@ -1465,17 +1550,8 @@ int lbm_halo_unpack(lbm_ctx *c)
     int rc = use_device(c);
     if (rc != LBM_OK) return rc;
     void *lat = c->f[c->cur];
-    const bool f32 = c->p.precision == LBM_F32;
-    if (c->halo_recv[0]) {
-        const long long pl = (c->z_begin - 1) - c->zs0;
-        LBM_CUDA(c, f32 ? halo_launch<float, false>(c, lat, c->halo_recv[0], pl, 1)
-                        : halo_launch<double, false>(c, lat, c->halo_recv[0], pl, 1));
-    }
-    if (c->halo_recv[1]) {
-        const long long pl = c->z_end - c->zs0;
-        LBM_CUDA(c, f32 ? halo_launch<float, false>(c, lat, c->halo_recv[1], pl, 0)
-                        : halo_launch<double, false>(c, lat, c->halo_recv[1], pl, 0));
-    }
+    if (c->halo_recv[0]) LBM_CUDA(c, halo_launch(c, lat, c->halo_recv[0], (c->z_begin - 1) - c->zs0, 1, false));
+    if (c->halo_recv[1]) LBM_CUDA(c, halo_launch(c, lat, c->halo_recv[1], c->z_end - c->zs0, 0, false));
     return LBM_OK;
 }
 

@@ -10,11 +10,12 @@
 // reference's IEEE operation order exactly (strict) or lets ptxas contract (fast, the -o switch).
 #pragma once
 
+// No standard-library headers: this file and lbm_kernels.cuh are also compiled at run time by NVRTC
+// (lbm_nvrtc.cu, the -D specialised variant), which has none.
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
 #include <stdint.h>
-
-#include <type_traits>
-#include <utility>
+#endif
 
 namespace lbm {
 
@@ -66,16 +67,23 @@ static_assert(opp(7) == 9 && opp(9) == 7 && opp(8) == 10 && opp(10) == 8, "opp")
 static_assert(opp(11) == 17 && opp(17) == 11 && opp(12) == 18 && opp(18) == 12, "opp");
 static_assert(opp(13) == 15 && opp(15) == 13 && opp(14) == 16 && opp(16) == 14, "opp");
 
-template <int... Is, typename F>
-__device__ __forceinline__ void static_for_impl(std::integer_sequence<int, Is...>, F &&f)
+// compile-time loop: f(IntC<0>{}) ... f(IntC<N-1>{}), fully unrolled; `decltype(arg)::value` is the index
+template <int V>
+struct IntC {
+    static constexpr int value = V;
+};
+template <int I, int N, typename F>
+__device__ __forceinline__ void static_for_step(F &f)
 {
-    (f(std::integral_constant<int, Is>{}), ...);
+    if constexpr (I < N) {
+        f(IntC<I>{});
+        static_for_step<I + 1, N>(f);
+    }
 }
-// f(std::integral_constant<int, 0>) ... f(std::integral_constant<int, N-1>), fully unrolled
 template <int N, typename F>
 __device__ __forceinline__ void static_for(F &&f)
 {
-    static_for_impl(std::make_integer_sequence<int, N>{}, static_cast<F &&>(f));
+    static_for_step<0, N>(f);
 }
 
 // ---- cell classification from coordinates (kernels.cl:236-266); 0 B of memory traffic ----

@@ -100,32 +100,13 @@ int lbm_group_create(const lbm_params *p, const int32_t *devices, int n, lbm_gro
         if (rc != LBM_OK) return bail(rc, std::string("slab ") + std::to_string(i) + ": " + lbm_last_error(nullptr));
         g->ctx.push_back(c);
     }
-    // peer access between neighbours on different devices
-    for (int i = 0; i < n; ++i) {
-        for (int d = -1; d <= 1; d += 2) {
-            const int j = i + d;
-            if (j < 0 || j >= n) continue;
-            const int di = g->ctx[i]->device, dj = g->ctx[j]->device;
-            if (di == dj) continue;
-            int can = 0;
-            if (cudaDeviceCanAccessPeer(&can, di, dj) != cudaSuccess || !can)
-                return bail(LBM_ERR_CUDA, "device " + std::to_string(di) + " cannot access peer " + std::to_string(dj));
-            cudaSetDevice(di);
-            const cudaError_t e = cudaDeviceEnablePeerAccess(dj, 0);
-            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
-            else if (e != cudaSuccess)
-                return bail(LBM_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess - ") + cudaGetErrorName(e));
-        }
-    }
+    // neighbours: peer access between the devices, each other's lattices as store targets
     for (int i = 0; i < n; ++i) {
         for (int face = 0; face < 2; ++face) {
             lbm_ctx *nb = face == 0 ? (i > 0 ? g->ctx[i - 1] : nullptr) : (i + 1 < n ? g->ctx[i + 1] : nullptr);
-            g->ctx[i]->peer[face] = nb;
-            if (nb) {
-                g->ctx[i]->peer_f[face][0] = nb->f[0];
-                g->ctx[i]->peer_f[face][1] = nb->f[1];
-                g->ctx[i]->peer_zs0[face] = nb->zs0;
-            }
+            if (!nb) continue;
+            const int rc = lbm_peer_attach(g->ctx[i], face, nb);  // peer access + the neighbour's lattices
+            if (rc != LBM_OK) return bail(rc, std::string("slab ") + std::to_string(i) + ": " + lbm_last_error(g->ctx[i]));
         }
     }
     g->bstream.assign(n, nullptr);
@@ -175,12 +156,8 @@ int lbm_group_run(lbm_group *g, int n_iterations, int every)
         lbm_ctx *c = g->ctx[i];
         if (!c->initialised) return gfail(g, LBM_ERR_STATE, "lbm_group_run before lbm_group_init");
         LBM_GCUDA(g, cudaSetDevice(c->device));
-        int rc = fold_events(c, false);
-        EventPair ep;
-        if (rc == LBM_OK) rc = push_pair(c, &ep);
+        const int rc = open_batch(c);
         if (rc != LBM_OK) return gfail(g, rc, "%s", lbm_last_error(c));
-        c->compute_events.push_back(ep);
-        LBM_GCUDA(g, cudaEventRecord(ep.start, c->stream));
         // the boundary stream starts after whatever the main stream was asked to do before
         LBM_GCUDA(g, cudaEventRecord(g->ev_join[i], c->stream));
         LBM_GCUDA(g, cudaStreamWaitEvent(g->bstream[i], g->ev_join[i], 0));
@@ -197,13 +174,11 @@ int lbm_group_run(lbm_group *g, int n_iterations, int every)
             if (has_lo) LBM_GCUDA(g, cudaStreamWaitEvent(bs, g->ev_b[prev][i - 1], 0));
             if (has_hi) LBM_GCUDA(g, cudaStreamWaitEvent(bs, g->ev_b[prev][i + 1], 0));
             LBM_GCUDA(g, cudaStreamWaitEvent(bs, g->ev_i[prev][i], 0));
-            const int zlo = c->z_begin, zhi = c->z_end - 1;
-            if (has_lo) LBM_GCUDA(g, launch_step(c, zlo, zlo + 1, macro, bs));
-            if (has_hi && !(has_lo && zhi == zlo)) LBM_GCUDA(g, launch_step(c, zhi, zhi + 1, macro, bs));
+            LBM_GCUDA(g, launch_step(c, boundary_planes(c), macro, PEER_STORE, bs));  // both faces, one launch
             LBM_GCUDA(g, cudaEventRecord(g->ev_b[par][i], bs));
 
             LBM_GCUDA(g, cudaStreamWaitEvent(c->stream, g->ev_b[prev][i], 0));
-            LBM_GCUDA(g, launch_step(c, zlo + (has_lo ? 1 : 0), c->z_end - (has_hi ? 1 : 0), macro, c->stream));
+            LBM_GCUDA(g, launch_step(c, interior_planes(c), macro, PEER_NONE, c->stream));
             LBM_GCUDA(g, cudaEventRecord(g->ev_i[par][i], c->stream));
         }
         for (lbm_ctx *c : g->ctx) {
@@ -216,8 +191,8 @@ int lbm_group_run(lbm_group *g, int n_iterations, int every)
         lbm_ctx *c = g->ctx[i];
         LBM_GCUDA(g, cudaSetDevice(c->device));
         LBM_GCUDA(g, cudaStreamWaitEvent(c->stream, g->ev_b[last][i], 0));
-        LBM_GCUDA(g, cudaEventRecord(c->compute_events.back().stop, c->stream));
-        LBM_GCUDA(g, cudaEventRecord(c->ev_last, c->stream));
+        const int rc = close_batch(c);
+        if (rc != LBM_OK) return gfail(g, rc, "%s", lbm_last_error(c));
     }
     return LBM_OK;
 }
@@ -241,6 +216,39 @@ int lbm_group_read_macros(lbm_group *g, void *rho_host, void *u_host)
     for (lbm_ctx *c : g->ctx) {
         rc = lbm_read_macros(c, rho_host, u_host);
         if (rc != LBM_OK) return gfail(g, rc, "%s", lbm_last_error(c));
+    }
+    return LBM_OK;
+}
+
+// The -f view over a group (reference storeF, lbmcl.hpp:206-258, has no single-device restriction because the
+// reference IS single-device): every slab renders the reference's pre-collision view of its owned planes
+// (its halo planes hold the neighbours' crossing populations), the host merges the owned cells.
+int lbm_group_read_f(lbm_group *g, void *f_host)
+{
+    if (!g || !f_host) return LBM_ERR_INVALID;
+    int rc = lbm_group_sync(g);
+    if (rc != LBM_OK) return rc;
+    lbm_ctx *c0 = g->ctx[0];
+    const long long dim = c0->dim, plane = dim * dim, n_cube = plane * dim;
+    const size_t es = c0->esize, bytes = (size_t)n_cube * Q * es;
+    std::vector<unsigned char> tmp(bytes);
+    unsigned char *out = static_cast<unsigned char *>(f_host);
+    for (lbm_ctx *c : g->ctx) {
+        if (!c->initialised) return gfail(g, LBM_ERR_STATE, "lbm_group_read_f before lbm_group_init");
+        LBM_GCUDA(g, cudaSetDevice(c->device));
+        void *d = nullptr;
+        LBM_GCUDA(g, cudaMalloc(&d, bytes));
+        cudaError_t e = enqueue_reference_view(c, d);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(tmp.data(), d, bytes, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        cudaFree(d);
+        LBM_GCUDA(g, e);
+        // owned cells of this slab, all 19 slots each, in the global CSoA order
+        const long long S = c->lay.qpitch();
+        for (long long id = (long long)c->z_begin * plane; id < (long long)c->z_end * plane; ++id) {
+            const long long b = c->lay.base(id);
+            for (int q = 0; q < Q; ++q) std::memcpy(out + (size_t)(b + q * S) * es, tmp.data() + (size_t)(b + q * S) * es, es);
+        }
     }
     return LBM_OK;
 }

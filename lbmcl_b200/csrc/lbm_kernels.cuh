@@ -38,14 +38,28 @@ struct alignas(sizeof(T) * N) Pack {
     T v[N];
 };
 
+// In-kernel ordering between neighbouring z-slabs that run in different processes / on different devices
+// (PEER == PEER_FLAGS): one 32-bit epoch word per face, written by the neighbour over NVLink when ALL blocks
+// of its boundary plane have stored their crossing populations, polled by the blocks of my boundary plane
+// before they gather from the halo plane.  No second stream, no events, no NCCL in the iteration loop.
+struct SlabSync {
+    unsigned *flag_in;         // [2] in MY memory: [0] written by the low neighbour, [1] by the high neighbour
+    unsigned *flag_out[2];     // the neighbours' words I write: [0] low neighbour's flag_in[1], [1] high's flag_in[0]
+    unsigned *count;           // [2] in my memory: boundary-plane blocks that have finished, per face
+    int *error;                // set to 1 when a wait ran into the time limit (lbm_sync reports it)
+    unsigned wait_epoch;       // the neighbours must have completed this phase before I touch the halo planes
+    unsigned signal_epoch;     // the phase this launch completes
+    unsigned long long timeout_ns;
+};
+
 template <typename T>
 struct StepArgs {
     T *__restrict__ dst;        // lattice written by this iteration      (G_k)
     const T *__restrict__ src;  // lattice gathered from                  (G_{k-1})
     T *__restrict__ rho;        // [n_local]
     T *__restrict__ u;          // [3][n_local]
-    // same-process z-slab neighbours: where the crossing populations of the first / last owned plane
-    // are ALSO stored (the neighbour's halo plane of the lattice it reads next), or nullptr
+    // z-slab neighbours: where the crossing populations of the first / last owned plane are ALSO stored
+    // (the neighbour's halo plane of the lattice it reads next), or nullptr
     T *__restrict__ peer_lo;    // receives q with e_z = -1 of plane z_own_begin
     T *__restrict__ peer_hi;    // receives q with e_z = +1 of plane z_own_end - 1
     long long peer_lo_plane;    // local plane index of that halo plane in the neighbour's storage
@@ -53,27 +67,67 @@ struct StepArgs {
     int z_own_begin, z_own_end; // owned global planes of this slab
     int dim;
     int zs0;                    // global z of local plane 0
-    int z_begin, z_end;         // global planes [z_begin, z_end) computed by this launch
+    // planes computed by this launch, in grid order: first zmap_n (0..2) individually named planes -- the
+    // slab's boundary planes, so that their crossing populations are on their way before the interior
+    // starts -- then the contiguous range [z_begin, z_end)
+    int zmap_n, zmap0, zmap1;
+    int z_begin, z_end;
     long long n_local;          // cells in local storage (pitch of the u components)
     Layout lay;
     Consts<T> c;
     T stale[2][Q];              // [0]: w_q (rest equilibrium); [1]: f_eq_q(1, (U,0,0)); see header
     // Byte offsets precomputed by the host (uniform; they live in the constant bank):
-    //   goff[q]  from the address of (x, y, z, 0) to the address of (x, y - ey, z - ez, q)   [LM_ROWS / LM_SOA]
-    //   soff[q]  from the address of (x, y, z, 0) to the address of (x, y, z, q)
+    //   goff[q]  LM_ROWS / LM_SOA: from the address of (x, y, z, 0) to the address of (x, y - ey, z - ez, q)
+    //   soff[q]  from the address of (x, y, z, 0) to the address of (x, y, z, q)      ( = q * stride * sizeof(T) )
     long long goff[Q];
     long long soff[Q];
     // AA variant, SHIFT step: from the address of (x + ex, y, z, 0) to the address of
     // (x + ex, y + ey, z + ez, q)
     long long poff[Q];
+    SlabSync sync;
 };
 
-// How neighbour addresses are formed (chosen by the host from stride and DIM):
-//   LM_GENERIC  any stride: full CSoA index computation per access;
-//   LM_ROWS     stride <= DIM: every x-row starts a CSoA block, so a shift in y or z is a constant
-//               address offset and only the x position inside the row needs the block arithmetic;
-//   LM_SOA      stride >= number of stored cells: one block, every neighbour is a constant offset.
-enum : int { LM_GENERIC = 0, LM_ROWS = 1, LM_SOA = 2 };
+// How neighbour addresses are formed (chosen by the host from stride and DIM; all strides are powers of two):
+//   LM_ROWS       stride <= DIM: every x-row starts a CSoA block, so a shift in y or z is a constant
+//                 address offset and only the x position inside the row needs the block arithmetic;
+//   LM_SOA        stride >= number of stored cells: one block, every neighbour is a constant offset;
+//   LM_BLOCKROWS  DIM < stride < stored cells: a whole x-row lies inside one CSoA block, so the thread
+//                 forms the 9 row bases (one per (e_y, e_z)) once; direction q is then base + q*stride and
+//                 the x shift is +-1 element;
+//   LM_GENERIC    full CSoA index computation per access (any stride; kept as a cross-check, test hook).
+enum : int { LM_GENERIC = 0, LM_ROWS = 1, LM_SOA = 2, LM_BLOCKROWS = 3 };
+
+// How the crossing populations of a slab's boundary planes reach the neighbour:
+//   PEER_NONE   not at all (single device, interior launches, dense-halo transports)
+//   PEER_STORE  stored straight into the neighbour's halo plane; ordering by CUDA events (same process)
+//   PEER_FLAGS  the same stores + the in-kernel epoch flags of SlabSync (one launch per iteration)
+enum : int { PEER_NONE = 0, PEER_STORE = 1, PEER_FLAGS = 2 };
+
+// Uniform quantities.  Ahead-of-time build: kernel arguments (constant bank).  Run-time specialised build
+// (NVRTC, lbm_nvrtc.cu -- the counterpart of the reference's -D kernel options, lbmcl.hpp:131-156):
+// literals, so that DIM, the stride, the 38 address offsets and the physical constants become instruction
+// immediates.
+#ifdef LBM_SPEC_DIM
+#define LBM_U_DIM(a) (LBM_SPEC_DIM)
+#define LBM_U_LAY(a) (Layout{LBM_SPEC_SDIV, (long long)(LBM_SPEC_STRIDE) - 1})
+#define LBM_U_ZS0(a) (0)
+#define LBM_U_NLOCAL(a) ((long long)(LBM_SPEC_DIM) * (LBM_SPEC_DIM) * (LBM_SPEC_DIM))
+#define LBM_U_CONSTS(T, a) (Consts<T>{T(LBM_SPEC_U_LID), T(LBM_SPEC_INV_TAU), {T(1.0) / T(3.0), T(1.0) / T(18.0), T(1.0) / T(36.0)}})
+#define LBM_U_SOFF(T, a, q) ((long long)(q) * (LBM_SPEC_STRIDE) * (long long)sizeof(T))
+#define LBM_U_GOFF(T, a, q, LM)                                                                              \
+    (((long long)(q) * (LBM_SPEC_STRIDE) -                                                                    \
+      ((LM) == LM_ROWS ? (long long)Q : 1ll) *                                                               \
+          ((long long)ey(q) * (LBM_SPEC_DIM) + (long long)ez(q) * (LBM_SPEC_DIM) * (LBM_SPEC_DIM))) *        \
+     (long long)sizeof(T))
+#else
+#define LBM_U_DIM(a) ((a).dim)
+#define LBM_U_LAY(a) ((a).lay)
+#define LBM_U_ZS0(a) ((a).zs0)
+#define LBM_U_NLOCAL(a) ((a).n_local)
+#define LBM_U_CONSTS(T, a) ((a).c)
+#define LBM_U_SOFF(T, a, q) ((a).soff[q])
+#define LBM_U_GOFF(T, a, q, LM) ((a).goff[q])
+#endif
 
 template <typename T>
 struct InitArgs {
@@ -235,52 +289,105 @@ __device__ __forceinline__ void bounce_back(T (&f)[Q])
     });
 }
 
-// One iteration.  Thread (tx, ty, tz) of block (bx, by, bz) owns the VEC cells
-//   x0 .. x0+VEC-1 = (blockIdx.x*bx + tx)*VEC .. ,  y = blockIdx.y*by + ty,  z = z_begin + blockIdx.z*bz + tz.
-// Requirements (checked by the host): bx a power of two, bx*VEC divides DIM, by divides DIM,
-// VEC divides stride (so every vector is aligned and inside one CSoA run).
-template <typename T, int VEC, bool FAST, bool MACRO, bool PEER, int LM>
-__global__ void __launch_bounds__(256) step_pull_kernel(const StepArgs<T> a)
+// ---- in-kernel slab ordering (PEER_FLAGS) ----
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// Wait until *flag has reached `epoch` (wrap-around safe).  Bounded: after timeout_ns the error word is set
+// and the caller carries on (the results are then wrong, lbm_sync reports it -- but the GPU never hangs).
+__device__ __forceinline__ void slab_wait(const unsigned *flag, unsigned epoch, unsigned long long timeout_ns, int *error)
+{
+    if ((int)(ld_acquire_sys(flag) - epoch) >= 0) return;
+    const unsigned long long t0 = global_timer_ns();
+    for (unsigned spins = 1;; ++spins) {
+        if ((int)(ld_acquire_sys(flag) - epoch) >= 0) return;
+        if ((spins & 0x3ffu) == 0 && global_timer_ns() - t0 > timeout_ns) {
+            if (error) atomicExch(error, 1);
+            return;
+        }
+    }
+}
+// Called by one thread per block after the block's stores (and a __syncthreads): the last of `n_blocks`
+// blocks publishes `epoch` in the neighbour's flag word.  fence / atomic / fence is the threadFenceReduction
+// pattern: every block's peer stores are ordered before the flag store of the last one.
+__device__ __forceinline__ void slab_signal(unsigned *count, unsigned n_blocks, unsigned *peer_flag, unsigned epoch)
+{
+    __threadfence_system();
+    const unsigned prev = atomicAdd(count, 1u);
+    if (prev == n_blocks - 1) {
+        atomicExch(count, 0u);  // ready for the next launch (stream order separates the launches)
+        __threadfence_system();
+        st_release_sys(peer_flag, epoch);
+    }
+}
+
+// One cell-group of one iteration: the thread owns the VEC cells x0 .. x0+VEC-1 of row (y, z).
+// `mask` = the lanes of the warp that execute this function (shuffles of the VEC > 1 variants).
+template <typename T, int VEC, bool FAST, bool MACRO, int PEER, int LM>
+__device__ __forceinline__ void step_pull_cells(const StepArgs<T> &a, const int x0, const int y, const int z,
+                                                const int rowbits, const unsigned mask)
 {
     using V = Pack<T, VEC>;
-    const int dim = a.dim;
+    const int dim = LBM_U_DIM(a);
+    const Layout lay = LBM_U_LAY(a);
+    const Consts<T> c = LBM_U_CONSTS(T, a);
+    const int zl = z - LBM_U_ZS0(a);
     const int tx = threadIdx.x;
-    const int x0 = (blockIdx.x * blockDim.x + tx) * VEC;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    const int z = a.z_begin + blockIdx.z * blockDim.z + threadIdx.z;
-
-    const int rowbits = (z < a.z_end) ? row_bits(y, z, dim) : CT_WALL;
-    const bool live = rowbits != CT_WALL;  // wall rows: never read, never written
-    const unsigned mask = __ballot_sync(0xffffffffu, live);
-    if (!live) return;
 
     const long long plane = (long long)dim * dim;
-    const long long id0 = x0 + (long long)y * dim + (long long)(z - a.zs0) * plane;
-    const long long qp = a.lay.qpitch();
+    const long long rowid = (long long)y * dim + (long long)zl * plane;  // id of the row's first cell
+    const long long id0 = x0 + rowid;
+    const long long qp = lay.qpitch();
 
-    // ---- addresses: one per-thread base, per-direction offsets are uniform ----
-    // b0 = element index of (x0, y, z, q = 0); bm / bp = of (x0 - 1, ..) and (x0 + VEC, ..), clamped
-    // into the row (the clamped values are only ever consumed by WALL cells).
-    long long b0, bm, bp;
+    // ---- addresses: per-thread bases, per-direction offsets are uniform ----
+    // LM_ROWS / LM_SOA: b0 = element index of (x0, y, z, q = 0); bm / bp = of (x0 - 1, ..) and (x0 + VEC, ..),
+    // clamped into the row (the clamped values are only ever consumed by WALL cells).
+    // LM_BLOCKROWS: rb[(ey+1)*3 + ez+1] = element index of (x0, y - ey, z - ez, q = 0); the x +- 1 neighbours
+    // are the adjacent elements (a row never leaves its CSoA block; reading one element past either end
+    // of a row stays inside the allocation and is only consumed by WALL cells).
+    long long b0, bm = 0, bp = 0;
+    long long rb[9];
     if constexpr (LM == LM_ROWS) {
-        const long long rowbase = ((long long)y * dim + (long long)(z - a.zs0) * plane) * Q;
+        const long long rowbase = rowid * Q;
         const int xm = x0 > 0 ? x0 - 1 : 0;
         const int xp = x0 + VEC < dim ? x0 + VEC : dim - 1;
-        const int sm = (int)a.lay.smod;
-        b0 = rowbase + ((((x0 >> a.lay.sdiv) * Q) << a.lay.sdiv) + (x0 & sm));
-        bm = rowbase + ((((xm >> a.lay.sdiv) * Q) << a.lay.sdiv) + (xm & sm));
-        bp = rowbase + ((((xp >> a.lay.sdiv) * Q) << a.lay.sdiv) + (xp & sm));
+        const int sm = (int)lay.smod;
+        b0 = rowbase + ((((x0 >> lay.sdiv) * Q) << lay.sdiv) + (x0 & sm));
+        bm = rowbase + ((((xm >> lay.sdiv) * Q) << lay.sdiv) + (xm & sm));
+        bp = rowbase + ((((xp >> lay.sdiv) * Q) << lay.sdiv) + (xp & sm));
     } else if constexpr (LM == LM_SOA) {
         b0 = id0;
         bm = id0 - 1;  // live rows have y >= 1, so id0 >= DIM
         bp = id0 + VEC;
+    } else if constexpr (LM == LM_BLOCKROWS) {
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+            for (int dz = -1; dz <= 1; ++dz)
+                rb[(dy + 1) * 3 + dz + 1] = lay.base(rowid - (long long)dy * dim - (long long)dz * plane) + x0;
+        b0 = rb[4];
     } else {
-        b0 = a.lay.base(id0);
-        bm = bp = 0;
+        b0 = lay.base(id0);
     }
     const char *const s0 = reinterpret_cast<const char *>(a.src + b0);
     const char *const sm1 = reinterpret_cast<const char *>(a.src + bm);
     const char *const sp1 = reinterpret_cast<const char *>(a.src + bp);
+    (void)sm1;
+    (void)sp1;
+    (void)rb;
 
     // ---- gather: f[q][j] = G(x0 + j - ex, y - ey, z - ez, q) ----
     T f[Q][VEC];
@@ -289,10 +396,13 @@ __global__ void __launch_bounds__(256) step_pull_kernel(const StepArgs<T> a)
             constexpr int q = decltype(qc)::value;
             if constexpr (LM == LM_GENERIC) {
                 const long long sid = id0 - ex(q) - (long long)ey(q) * dim - (long long)ez(q) * plane;
-                f[q][0] = a.src[a.lay.base(sid) + q * qp];
+                f[q][0] = a.src[lay.base(sid) + q * qp];
+            } else if constexpr (LM == LM_BLOCKROWS) {
+                const char *p = reinterpret_cast<const char *>(a.src + rb[(ey(q) + 1) * 3 + ez(q) + 1]);
+                f[q][0] = *(reinterpret_cast<const T *>(p + LBM_U_SOFF(T, a, q)) - ex(q));
             } else {
                 const char *p = ex(q) == 0 ? s0 : (ex(q) == 1 ? sm1 : sp1);
-                f[q][0] = *reinterpret_cast<const T *>(p + a.goff[q]);
+                f[q][0] = *reinterpret_cast<const T *>(p + LBM_U_GOFF(T, a, q, LM));
             }
         });
     } else {
@@ -307,13 +417,19 @@ __global__ void __launch_bounds__(256) step_pull_kernel(const StepArgs<T> a)
             if constexpr (LM == LM_GENERIC) {
                 const long long sid = id0 - (long long)ey(q) * dim - (long long)ez(q) * plane;
                 const T *p = a.src + q * qp;
-                v = *reinterpret_cast<const V *>(p + a.lay.base(sid));
-                pe_m = p + (ex(q) == 1 ? a.lay.base(sid - 1) : 0);
-                pe_p = p + (ex(q) == -1 ? a.lay.base(sid + VEC) : 0);
+                v = *reinterpret_cast<const V *>(p + lay.base(sid));
+                pe_m = p + (ex(q) == 1 ? lay.base(sid - 1) : 0);
+                pe_p = p + (ex(q) == -1 ? lay.base(sid + VEC) : 0);
+            } else if constexpr (LM == LM_BLOCKROWS) {
+                const char *p = reinterpret_cast<const char *>(a.src + rb[(ey(q) + 1) * 3 + ez(q) + 1]);
+                const T *pv = reinterpret_cast<const T *>(p + LBM_U_SOFF(T, a, q));
+                v = *reinterpret_cast<const V *>(pv);
+                pe_m = pv - 1;
+                pe_p = pv + VEC;
             } else {
-                v = *reinterpret_cast<const V *>(s0 + a.goff[q]);
-                pe_m = reinterpret_cast<const T *>(sm1 + a.goff[q]);
-                pe_p = reinterpret_cast<const T *>(sp1 + a.goff[q]);
+                v = *reinterpret_cast<const V *>(s0 + LBM_U_GOFF(T, a, q, LM));
+                pe_m = reinterpret_cast<const T *>(sm1 + LBM_U_GOFF(T, a, q, LM));
+                pe_p = reinterpret_cast<const T *>(sp1 + LBM_U_GOFF(T, a, q, LM));
             }
             if constexpr (ex(q) == 0) {
 #pragma unroll
@@ -371,10 +487,10 @@ __global__ void __launch_bounds__(256) step_pull_kernel(const StepArgs<T> a)
         for (int q = 0; q < Q; ++q) fc[q] = f[q][j];
         T rho = nan, ux = nan, uy = nan, uz = nan;
         if (t == CT_FLUID) {
-            collide_fluid<T, FAST>(fc, a.c, rho, ux, uy, uz);
+            collide_fluid<T, FAST>(fc, c, rho, ux, uy, uz);
         } else if (t & CT_MOVING) {
-            collide_lid<T, FAST>(fc, a.c, rho);
-            ux = a.c.u_lid;
+            collide_lid<T, FAST>(fc, c, rho);
+            ux = c.u_lid;
             uy = T(0);
             uz = T(0);
         } else if (is_bounceback(t)) {
@@ -395,28 +511,42 @@ __global__ void __launch_bounds__(256) step_pull_kernel(const StepArgs<T> a)
         V v;
 #pragma unroll
         for (int j = 0; j < VEC; ++j) v.v[j] = f[q][j];
-        *reinterpret_cast<V *>(d0 + a.soff[q]) = v;
-        if constexpr (PEER) {
-            // fused halo exchange: the five populations that cross the slab face also go straight
-            // into the neighbour's halo plane (NVLink stores when the neighbour is a peer device)
-            if constexpr (ez(q) == -1) {
-                if (a.peer_lo != nullptr && z == a.z_own_begin) {
-                    const long long pid = x0 + (long long)y * dim + a.peer_lo_plane * plane;
-                    *reinterpret_cast<V *>(a.peer_lo + a.lay.base(pid) + q * qp) = v;
-                }
-            } else if constexpr (ez(q) == 1) {
-                if (a.peer_hi != nullptr && z == a.z_own_end - 1) {
-                    const long long pid = x0 + (long long)y * dim + a.peer_hi_plane * plane;
-                    *reinterpret_cast<V *>(a.peer_hi + a.lay.base(pid) + q * qp) = v;
-                }
-            }
-        }
+        *reinterpret_cast<V *>(d0 + LBM_U_SOFF(T, a, q)) = v;
     });
+    if constexpr (PEER != PEER_NONE) {
+        // fused halo exchange: the five populations that cross a slab face also go straight into the
+        // neighbour's halo plane (NVLink stores when the neighbour is a peer device); plane-uniform branches
+        if (a.peer_lo != nullptr && z == a.z_own_begin) {
+            T *const p = a.peer_lo + lay.base(x0 + (long long)y * dim + a.peer_lo_plane * plane);
+            static_for<Q>([&](auto qc) {
+                constexpr int q = decltype(qc)::value;
+                if constexpr (ez(q) == -1) {
+                    V v;
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) v.v[j] = f[q][j];
+                    *reinterpret_cast<V *>(p + q * qp) = v;
+                }
+            });
+        }
+        if (a.peer_hi != nullptr && z == a.z_own_end - 1) {
+            T *const p = a.peer_hi + lay.base(x0 + (long long)y * dim + a.peer_hi_plane * plane);
+            static_for<Q>([&](auto qc) {
+                constexpr int q = decltype(qc)::value;
+                if constexpr (ez(q) == 1) {
+                    V v;
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) v.v[j] = f[q][j];
+                    *reinterpret_cast<V *>(p + q * qp) = v;
+                }
+            });
+        }
+    }
 
     // ---- macro store (kernels.cl:383-388): only FLUID / MOVING cells; the others keep their NaN ----
     if constexpr (MACRO) {
         const bool row_stores = !(rowbits & (CT_TOP | CT_BOTTOM | CT_BACK));
         if (row_stores) {
+            const long long n_local = LBM_U_NLOCAL(a);
             V r, vx, vy, vz;
 #pragma unroll
             for (int j = 0; j < VEC; ++j) {
@@ -427,10 +557,81 @@ __global__ void __launch_bounds__(256) step_pull_kernel(const StepArgs<T> a)
             }
             *reinterpret_cast<V *>(a.rho + id0) = r;
             *reinterpret_cast<V *>(a.u + id0) = vx;
-            *reinterpret_cast<V *>(a.u + a.n_local + id0) = vy;
-            *reinterpret_cast<V *>(a.u + 2 * a.n_local + id0) = vz;
+            *reinterpret_cast<V *>(a.u + n_local + id0) = vy;
+            *reinterpret_cast<V *>(a.u + 2 * n_local + id0) = vz;
         }
     }
+}
+
+// One iteration.  Thread (tx, ty, tz) of block (bx, by, bz) owns the VEC cells
+//   x0 .. x0+VEC-1 = (blockIdx.x*bx + tx)*VEC .. ,  y = blockIdx.y*by + ty,  plane number blockIdx.z*bz + tz
+// of the launch's plane list (StepArgs::zmap*, z_begin, z_end).
+// Requirements (checked by the host): bx a power of two, bx*VEC divides DIM, by divides DIM,
+// VEC divides stride (so every vector is aligned and inside one CSoA run); PEER_FLAGS: bz == 1.
+template <typename T, int VEC, bool FAST, bool MACRO, int PEER, int LM>
+__device__ __forceinline__ void step_pull_body(const StepArgs<T> &a)
+{
+    const int dim = LBM_U_DIM(a);
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int zi = blockIdx.z * blockDim.z + threadIdx.z;
+    int z;
+    bool zok = true;
+    if (zi < a.zmap_n) {
+        z = zi == 0 ? a.zmap0 : a.zmap1;
+    } else {
+        z = a.z_begin + (zi - a.zmap_n);
+        zok = z < a.z_end;
+    }
+    const int rowbits = zok ? row_bits(y, z, dim) : CT_WALL;
+    const bool live = rowbits != CT_WALL;  // wall rows: never read, never written
+    const unsigned mask = __ballot_sync(0xffffffffu, live);
+
+    if constexpr (PEER == PEER_FLAGS) {
+        // block-uniform (bz == 1): is this block part of a boundary plane that talks to a neighbour?
+        const bool lo_face = a.peer_lo != nullptr && z == a.z_own_begin;
+        const bool hi_face = a.peer_hi != nullptr && z == a.z_own_end - 1;
+        const bool first = threadIdx.x == 0 && threadIdx.y == 0;
+        if (lo_face || hi_face) {
+            // the halo plane I gather from holds the neighbour's populations of the previous phase, and the
+            // neighbour has finished reading the halo plane I am about to overwrite
+            if (first) {
+                if (lo_face) slab_wait(a.sync.flag_in + 0, a.sync.wait_epoch, a.sync.timeout_ns, a.sync.error);
+                if (hi_face) slab_wait(a.sync.flag_in + 1, a.sync.wait_epoch, a.sync.timeout_ns, a.sync.error);
+            }
+            __syncthreads();
+        }
+        if (live) step_pull_cells<T, VEC, FAST, MACRO, PEER, LM>(a, x0, y, z, rowbits, mask);
+        if (lo_face || hi_face) {
+            __syncthreads();
+            if (first) {
+                const unsigned n_blocks = gridDim.x * gridDim.y;
+                if (lo_face) slab_signal(a.sync.count + 0, n_blocks, a.sync.flag_out[0], a.sync.signal_epoch);
+                if (hi_face) slab_signal(a.sync.count + 1, n_blocks, a.sync.flag_out[1], a.sync.signal_epoch);
+            }
+        }
+    } else {
+        if (!live) return;
+        step_pull_cells<T, VEC, FAST, MACRO, PEER, LM>(a, x0, y, z, rowbits, mask);
+    }
+}
+
+// Occupancy: the fp32 one-cell-per-thread kernel needs 40 registers (6 blocks of 256 threads per SM).
+// The neighbour code of the PEER variants takes it to 48 (5 blocks); building with -DLBM_PEER_TIGHT caps
+// them at 40 as well, at the price of 16-40 bytes of spill (A/B-measured, see profiles/).
+#ifndef LBM_PEER_TIGHT
+#define LBM_PEER_TIGHT 0
+#endif
+template <typename T, int VEC, bool MACRO, int PEER>
+__host__ __device__ constexpr int step_min_blocks()
+{
+    return (sizeof(T) == 4 && VEC == 1 && !MACRO && (PEER == PEER_NONE || LBM_PEER_TIGHT)) ? 6 : 1;
+}
+
+template <typename T, int VEC, bool FAST, bool MACRO, int PEER, int LM>
+__global__ void __launch_bounds__(256, step_min_blocks<T, VEC, MACRO, PEER>()) step_pull_kernel(const StepArgs<T> a)
+{
+    step_pull_body<T, VEC, FAST, MACRO, PEER, LM>(a);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -456,13 +657,15 @@ __global__ void __launch_bounds__(256) step_aa_kernel(const StepArgs<T> a)
     if (rowbits == CT_WALL || x == 0 || x >= dim - 1) return;  // WALL cells neither read nor write
 
     const long long plane = (long long)dim * dim;
-    const long long id0 = x + (long long)y * dim + (long long)(z - a.zs0) * plane;
+    const long long rowid = (long long)y * dim + (long long)(z - a.zs0) * plane;
+    const long long id0 = x + rowid;
     const long long qp = a.lay.qpitch();
     T *const lat = a.dst;
 
     long long b0, bm = 0, bp = 0;
+    long long rb[9];  // LM_BLOCKROWS, SHIFT: element index of (x, y - dy, z - dz, q = 0), see step_pull_cells
     if constexpr (LM == LM_ROWS) {
-        const long long rowbase = ((long long)y * dim + (long long)(z - a.zs0) * plane) * Q;
+        const long long rowbase = rowid * Q;
         const int sm = (int)a.lay.smod;
         b0 = rowbase + ((((x >> a.lay.sdiv) * Q) << a.lay.sdiv) + (x & sm));
         if constexpr (SHIFT) {
@@ -473,9 +676,19 @@ __global__ void __launch_bounds__(256) step_aa_kernel(const StepArgs<T> a)
         b0 = id0;
         bm = id0 - 1;
         bp = id0 + 1;
+    } else if constexpr (LM == LM_BLOCKROWS) {
+        b0 = a.lay.base(rowid) + x;
+        if constexpr (SHIFT) {
+#pragma unroll
+            for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                for (int dz = -1; dz <= 1; ++dz)
+                    rb[(dy + 1) * 3 + dz + 1] = a.lay.base(rowid - (long long)dy * dim - (long long)dz * plane) + x;
+        }
     } else {
         b0 = a.lay.base(id0);
     }
+    (void)rb;
     char *const c0 = reinterpret_cast<char *>(lat + b0);
     char *const cm = reinterpret_cast<char *>(lat + bm);
     char *const cp = reinterpret_cast<char *>(lat + bp);
@@ -491,6 +704,14 @@ __global__ void __launch_bounds__(256) step_aa_kernel(const StepArgs<T> a)
                 ? id0 + ex(q) + (long long)ey(q) * dim + (long long)ez(q) * plane
                 : id0 - ex(q) - (long long)ey(q) * dim - (long long)ez(q) * plane;
             return lat + a.lay.base(nid) + (for_store ? q : opp(q)) * qp;
+        } else if constexpr (LM == LM_BLOCKROWS) {
+            // SHIFT: read (c - e_q, opp(q)), write (c + e_q, q)
+            if (for_store) {
+                char *p = reinterpret_cast<char *>(lat + rb[(-ey(q) + 1) * 3 - ez(q) + 1]);
+                return reinterpret_cast<T *>(p + a.soff[q]) + ex(q);
+            }
+            char *p = reinterpret_cast<char *>(lat + rb[(ey(q) + 1) * 3 + ez(q) + 1]);
+            return reinterpret_cast<T *>(p + a.soff[opp(q)]) - ex(q);
         } else {
             // SHIFT: read (c - e_q, opp(q)), write (c + e_q, q): the same address for q and opp(q) swapped
             if (for_store) return reinterpret_cast<T *>((ex(q) == 0 ? c0 : (ex(q) == 1 ? cp : cm)) + a.poff[q]);
@@ -608,16 +829,6 @@ __global__ void __launch_bounds__(256) reference_view_aa_kernel(const T *__restr
         }
         out[lay.base(gid) + q * lay.qpitch()] = v;
     });
-}
-
-// Cell-type map (kernels.cl:290), only for the -m dump.
-__global__ void map_kernel(int *__restrict__ map, int dim)
-{
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    const int z = blockIdx.z;
-    if (x >= dim || y >= dim) return;
-    map[x + (long long)y * dim + (long long)z * dim * dim] = cell_type(x, y, z, dim);
 }
 
 // Reference view of the lattice the next iteration reads (for the -f dump, lbmcl.hpp:206-258):

@@ -1,0 +1,105 @@
+// Instantiations of the TMA-fed step kernels (lbm_tma.cuh) and their launch glue.
+#include "lbm_launch.hpp"
+#include "lbm_tma.cuh"
+
+namespace lbm {
+
+namespace {
+
+constexpr int TMA_SMEM_MAX = 200 * 1024;
+
+template <typename T, int TX>
+cudaError_t prepare_tx()
+{
+    cudaError_t e = cudaSuccess;
+#define LBM_TMA_ATTR(F, M)                                                                                   \
+    if (e == cudaSuccess)                                                                                    \
+        e = cudaFuncSetAttribute(step_tma_kernel<T, F, M, TX>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                 TMA_SMEM_MAX)
+    LBM_TMA_ATTR(false, false);
+    LBM_TMA_ATTR(false, true);
+    LBM_TMA_ATTR(true, false);
+    LBM_TMA_ATTR(true, true);
+#undef LBM_TMA_ATTR
+    return e;
+}
+
+template <typename T>
+cudaError_t prepare_t()
+{
+    cudaError_t e = prepare_tx<T, 256>();
+    if (e == cudaSuccess) e = prepare_tx<T, 128>();
+    if (e == cudaSuccess) e = prepare_tx<T, 64>();
+    if (e == cudaSuccess) e = prepare_tx<T, 32>();
+    return e;
+}
+
+template <typename T, int TX>
+void go(const TmaCfg &k, const TmaArgs<T> &a, bool macro, int grid, cudaStream_t s)
+{
+    const CUtensorMap &ms = *k.map_src, &md = *k.map_dst;
+    if (k.fast) {
+        if (macro) step_tma_kernel<T, true, true, TX><<<grid, TX, k.smem, s>>>(ms, md, a, k.error);
+        else step_tma_kernel<T, true, false, TX><<<grid, TX, k.smem, s>>>(ms, md, a, k.error);
+    } else {
+        if (macro) step_tma_kernel<T, false, true, TX><<<grid, TX, k.smem, s>>>(ms, md, a, k.error);
+        else step_tma_kernel<T, false, false, TX><<<grid, TX, k.smem, s>>>(ms, md, a, k.error);
+    }
+}
+
+template <typename T>
+cudaError_t launch_tma(const TmaCfg &k, const StepArgs<T> &sa, int ns, bool macro, cudaStream_t s)
+{
+    // live planes of this launch (the TMA kernels take one contiguous range)
+    const int zf = sa.z_begin < 1 ? 1 : sa.z_begin;
+    const int zl = sa.z_end > sa.dim - 1 ? sa.dim - 1 : sa.z_end;
+    if (zl <= zf) return cudaSuccess;
+    TmaArgs<T> a{};
+    a.src = sa.src;
+    a.rho = sa.rho;
+    a.u = sa.u;
+    a.dim = sa.dim;
+    a.zs0 = sa.zs0;
+    a.z_first = zf;
+    a.n_xseg = sa.dim / k.tx;
+    a.n_tiles = (zl - zf) * (sa.dim - 2) * a.n_xseg;
+    a.ns = ns;
+    a.n_local = sa.n_local;
+    a.lay = sa.lay;
+    a.c = sa.c;
+    for (int i = 0; i < 2; ++i)
+        for (int q = 0; q < Q; ++q) a.stale[i][q] = sa.stale[i][q];
+    const int grid = a.n_tiles < k.grid ? a.n_tiles : k.grid;
+    switch (k.tx) {
+        case 256: go<T, 256>(k, a, macro, grid, s); break;
+        case 128: go<T, 128>(k, a, macro, grid, s); break;
+        case 64: go<T, 64>(k, a, macro, grid, s); break;
+        default: go<T, 32>(k, a, macro, grid, s); break;
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+// The opt-in to more than 48 KB of dynamic shared memory is per function and per device; done once per
+// device when the first TMA context is created there (not per launch: launches may be inside a stream capture).
+cudaError_t tma_prepare(int device)
+{
+    static bool done[64] = {};
+    if (device >= 0 && device < 64 && done[device]) return cudaSuccess;
+    cudaError_t e = prepare_t<float>();
+    if (e == cudaSuccess) e = prepare_t<double>();
+    if (e == cudaSuccess && device >= 0 && device < 64) done[device] = true;
+    return e;
+}
+
+cudaError_t launch_tma_f32(const TmaCfg &k, const StepArgs<float> &a, int ns, bool macro, cudaStream_t s)
+{
+    return launch_tma<float>(k, a, ns, macro, s);
+}
+cudaError_t launch_tma_f64(const TmaCfg &k, const StepArgs<double> &a, int ns, bool macro, cudaStream_t s)
+{
+    return launch_tma<double>(k, a, ns, macro, s);
+}
+
+}  // namespace lbm

@@ -151,13 +151,15 @@ __global__ void __launch_bounds__(TX) step_tma_kernel(const __grid_constant__ CU
         const uint32_t parity = (uint32_t)(i / NS) & 1u;
         T *const tile = ring + (size_t)s * Q * TX;
 
-        // bounded wait: a TMA fault must not hang the GPU
+        // bounded wait: a TMA fault must not hang the GPU.  A thread that runs into the limit carries on
+        // with whatever the tile holds; the CTA leaves together at the barrier below.
+        bool timed_out = false;
         {
             long long spins = 0;
             while (!mbar_try_wait(&full[s], parity)) {
                 if (++spins > (1ll << 22)) {
-                    if (error_flag) atomicExch(error_flag, 1);
-                    return;
+                    timed_out = true;
+                    break;
                 }
             }
         }
@@ -205,7 +207,11 @@ __global__ void __launch_bounds__(TX) step_tma_kernel(const __grid_constant__ CU
                 });
             }
         }
-        __syncthreads();  // every thread has taken its inputs: the tile may be overwritten in place
+        // every thread has taken its inputs: the tile may be overwritten in place
+        if (__syncthreads_or(timed_out ? 1 : 0)) {  // CTA-uniform exit
+            if (tx == 0 && error_flag) atomicExch(error_flag, 1);
+            return;
+        }
 
         const int t = cell_type_from_row(rowbits, x, dim);
         T rho = nan, ux = nan, uy = nan, uz = nan;

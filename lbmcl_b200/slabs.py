@@ -57,27 +57,47 @@ def exchange_halos(send, recv, world: int, rank: int, group=None):
     return dist.batch_isend_irecv(ops) if ops else []
 
 
-def connect_slabs(sim, rank: int, world: int, device, fused: bool = True) -> str:
-    """Give the slab context `sim` its library-owned NCCL communicator and, if possible, the fused
-    peer-store transport.  torch.distributed is used only as the bootstrap channel: it broadcasts the
-    128-byte NCCL id, gathers the CUDA IPC blobs and agrees on the transport.  Returns the transport in
-    use: "peer-stores+token" or "nccl-dense"."""
+TRANSPORTS = ("flags", "token", "dense")
+
+
+def connect_slabs(sim, rank: int, world: int, device, transport: str = "flags") -> str:
+    """Connect the slab context `sim` to its neighbours in the other ranks.  torch.distributed (whatever
+    backend the process group has: NCCL on the GPUs, gloo works too) is only the bootstrap channel.
+
+      "flags"  CUDA IPC peer stores + in-kernel epoch flags: one launch per iteration, no NCCL at all
+               (include/lbm_b200.h transport 2c);
+      "token"  CUDA IPC peer stores + a library-owned NCCL communicator carrying one word per face (2d);
+      "dense"  packed halos over the library-owned NCCL communicator (2b).
+
+    If a rank cannot attach a neighbour (no peer access), every rank detaches again and the dense transport is
+    used.  Returns the transport in use: "peer-stores+flags", "peer-stores+token" or "nccl-dense"."""
     import torch
     import torch.distributed as dist
-    from .capi import LbmError, Simulation
+    from .capi import FUSED_FLAGS, FUSED_TOKEN, LbmError, Simulation
 
-    uid = torch.zeros(128, dtype=torch.uint8, device=device)
-    if rank == 0:
-        uid.copy_(torch.frombuffer(bytearray(Simulation.comm_unique_id()), dtype=torch.uint8))
-    dist.broadcast(uid, 0)
-    sim.comm_init(uid.cpu().numpy().tobytes(), rank, world)
-    if not fused or world < 2:
+    if transport not in TRANSPORTS:
+        raise ValueError(f"transport {transport!r}: expected one of {TRANSPORTS}")
+    where = device if dist.get_backend() == "nccl" else torch.device("cpu")
+
+    def comm_init():
+        uid = torch.zeros(128, dtype=torch.uint8, device=where)
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(Simulation.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        sim.comm_init(uid.cpu().numpy().tobytes(), rank, world)
+
+    if world < 2:
+        return "single"
+    if transport == "dense":
+        comm_init()
         return "nccl-dense"
+    if transport == "token":
+        comm_init()
     ok = 1
     try:
-        blob = torch.frombuffer(bytearray(sim.ipc_export()), dtype=torch.uint8).to(device)
+        blob = torch.frombuffer(bytearray(sim.ipc_export()), dtype=torch.uint8).to(where)
     except LbmError:
-        blob = torch.zeros(Simulation.IPC_BYTES, dtype=torch.uint8, device=device)
+        blob = torch.zeros(Simulation.IPC_BYTES, dtype=torch.uint8, device=where)
         ok = 0
     blobs = [torch.empty_like(blob) for _ in range(world)]
     dist.all_gather(blobs, blob)
@@ -90,9 +110,14 @@ def connect_slabs(sim, rank: int, world: int, device, fused: bool = True) -> str
                 sim.ipc_attach(FACE_HIGH, blobs[hi].cpu().numpy().tobytes())
         except LbmError:
             ok = 0
-    flag = torch.tensor([ok], device=device, dtype=torch.int32)
+    flag = torch.tensor([ok], device=where, dtype=torch.int32)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if int(flag.item()) == 1:
-        sim.comm_fused(True)
-        return "peer-stores+token"
+        sim.comm_fused(FUSED_FLAGS if transport == "flags" else FUSED_TOKEN)
+        return "peer-stores+flags" if transport == "flags" else "peer-stores+token"
+    # some rank could not attach: nobody keeps a mapping (a half-attached slab must not store into its
+    # neighbour while the dense halos travel as well), everybody falls back to the dense transport
+    sim.ipc_detach()
+    if transport == "flags":
+        comm_init()
     return "nccl-dense"
