@@ -26,6 +26,14 @@ def _np_ptr(a):
     return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
 
 
+def host_cores() -> int:
+    """Cores this process may run on (affinity-aware)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def n_snapshots(iterations: int, every: int) -> int:
     """Number of rho/u snapshots the reference host writes (lbmcl.hpp:502, 513-515)."""
     return 0 if every == 0 else 1 + iterations // every
@@ -64,6 +72,12 @@ class Oracle:
         self._run.restype = ctypes.c_int
         lib.lbm_oracle_map.argtypes = [ctypes.c_int, vp]
         lib.lbm_oracle_map.restype = None
+        lib.lbm_oracle_set_threads.argtypes = [ctypes.c_int]
+        lib.lbm_oracle_set_threads.restype = ctypes.c_int
+
+    def set_threads(self, n: int) -> int:
+        """Ask for n OpenMP threads (overrides OMP_NUM_THREADS); returns the number in effect."""
+        return Oracle._lib.lbm_oracle_set_threads(n)
 
     def params(self, nu: float, u_lid: float):
         out = np.zeros(3, dtype=np.float64)
@@ -148,6 +162,12 @@ class RefKernel:
         self.lib.ref_compute.restype = None
         self.lib.ref_run.argtypes = [vp] * 5 + [ctypes.c_int, ctypes.c_int, vp, vp]
         self.lib.ref_run.restype = ctypes.c_int
+        self.lib.ref_set_threads.argtypes = [ctypes.c_int]
+        self.lib.ref_set_threads.restype = ctypes.c_int
+
+    def set_threads(self, n: int) -> int:
+        """Ask for n OpenMP threads (overrides OMP_NUM_THREADS); returns the number in effect."""
+        return self.lib.ref_set_threads(n)
 
     @property
     def viscosity(self) -> float:

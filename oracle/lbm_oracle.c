@@ -14,6 +14,9 @@
  * Every function names the reference lines it follows (paths relative to /root/reference).
  * Build: see oracle/Makefile (-ffp-contract=off, no fast-math: SURVEY F10/F11).
  */
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -100,6 +103,18 @@ static double text_roundtrip_f64(double v)
 #undef REAL
 #undef SUF
 #undef ROUNDTRIP
+
+/* Thread count of the z-parallel loops (launchers such as torchrun export OMP_NUM_THREADS=1). */
+int lbm_oracle_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
 
 /* cell-type map only (kernels.cl:290) */
 void lbm_oracle_map(int dim, int *map)

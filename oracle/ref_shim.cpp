@@ -16,6 +16,9 @@
 #include <cmath>
 #include <cstddef>
 #include <cstring>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #define __kernel
 #define __global
@@ -37,6 +40,19 @@ int ref_stride(void) { return STRIDE_MOD + 1; }
 int ref_sizeof_real(void) { return (int)sizeof(real_t); }
 double ref_viscosity(void) { return (double)(real_t)VISCOSITY; }
 double ref_velocity(void) { return (double)(real_t)VELOCITY; }
+
+// Thread count of the z-parallel loops below.  Launchers such as torchrun export OMP_NUM_THREADS=1; the
+// CPU-baseline legs of bench.py ask for the cores explicitly and report what they really got.
+int ref_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
 
 // kernels.cl:277-318 over the NDRange (DIM,DIM,DIM) of lbmcl.hpp:371,495
 void ref_initialize(real_t *f_stream, real_t *f_collide, real_t *density, real_t *u, int *map)

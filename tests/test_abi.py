@@ -84,3 +84,14 @@ def test_product_path_does_not_touch_the_oracle():
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "import oracle" not in text and "from oracle import" not in text, f
                 assert "liblbm_oracle" not in text and "oracle/_ref" not in text, f
+
+
+def test_specialised_kernel_source_builds_without_a_gpu():
+    """LBM_VARIANT_NVRTC's translation unit (the embedded kernel headers + -D options, the counterpart of the
+    reference's run-time OpenCL build, lbmcl.hpp:131-156) compiles for sm_100a on a GPU-less box."""
+    from lbmcl_b200 import capi
+    for kw in (dict(dim=256, stride=32, precision="f32"), dict(dim=64, stride=4096, precision="f64", fast_math=True),
+               dict(dim=16, stride=4096, precision="f32")):
+        cubin = capi.spec_cubin(**kw)
+        assert cubin[:4] == b"\x7fELF" and len(cubin) > 10000
+        assert b"lbm_step_spec_m0" in cubin and b"lbm_step_spec_m1" in cubin

@@ -94,10 +94,28 @@ def test_block_shapes(block):
 
 @pytest.mark.parametrize("precision", ["f32", "f64"])
 @pytest.mark.parametrize("variant", [1, 2, 4, 8])
+@pytest.mark.parametrize("stride", [64, 1024, 16384])
+def test_row_base_addressing_for_strides_between_dim_and_cells(stride, variant, precision):
+    """DIM < stride < stored cells (LM_BLOCKROWS: 9 row bases per thread instead of a CSoA index per access):
+    e.g. every `-s 64/128` of the reference's sweep at DIM <= 32..64, or -s DIM^2.  Bit-identical to the oracle,
+    rho/u snapshots and the -f view, odd and even iteration counts (AA: LOCAL and SHIFT steps)."""
+    dim, every = 32, 3
+    for its in (6, 7):
+        exp = Oracle(precision).run(dim, stride, 0.0089, 0.05, its, every, keep_state=True)
+        with _sim(dim=dim, precision=precision, stride=stride, variant=variant) as s:
+            rho, u = s.run_snapshots(its, every)
+            got_f = s.read_f()
+        assert rho.tobytes() == exp["rho"].tobytes() and u.tobytes() == exp["u"].tobytes(), its
+        st = exp["state"]
+        assert got_f.tobytes() == (st["f_stream"] if (its + 1) % 2 == 0 else st["f_collide"]).tobytes(), its
+
+
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+@pytest.mark.parametrize("variant", [1, 2, 4, 8])
 def test_generic_addressing_equals_fast_addressing(variant, precision):
-    """LM_GENERIC (any stride) and LM_ROWS / LM_SOA (uniform offsets) are the same function."""
+    """LM_GENERIC (any stride) and LM_ROWS / LM_SOA / LM_BLOCKROWS (uniform offsets) are the same function."""
     dim, its, every = 32, 6, 3
-    for stride in (32, 8, 32768):
+    for stride in (32, 8, 32768, 1024):
         exp = Oracle(precision).run(dim, stride, 0.0089, 0.05, its, every)
         with _sim(dim=dim, precision=precision, stride=stride, variant=variant, generic_addressing=True) as s:
             rho, u = s.run_snapshots(its, every)
@@ -220,6 +238,102 @@ def test_slab_group_on_one_device_matches_single():
         assert u.tobytes() == exp["u"].tobytes(), n
 
 
+@pytest.mark.parametrize("precision,stride", [("f32", 32), ("f64", 32), ("f32", 2048), ("f64", 1)])
+def test_flag_transport_between_two_contexts_on_one_device(precision, stride, monkeypatch):
+    """The one-launch-per-iteration transport (peer stores + in-kernel epoch flags, include/lbm_b200.h 2c) with
+    both slabs in this process on device 0 (lbm_peer_attach): each context runs on its own stream, the kernels
+    meet only through the flag words.  Re-initialisation is a phase of the protocol and needs no barrier.
+    (The grids are small enough to be co-resident, which the polling relies on.)"""
+    from lbmcl_b200.capi import FUSED_FLAGS, Simulation
+    monkeypatch.setenv("LBM_SYNC_TIMEOUT_S", "5")   # a broken protocol fails in seconds, not minutes
+    dim, its, every = 32, 11, 4
+    exp = Oracle(precision).run(dim, stride, 0.0089, 0.05, its, every)
+    parts = [(0, 8), (8, 24), (24, 32)]
+    sims = [Simulation(dim=dim, precision=precision, stride=stride, z_range=z) for z in parts]
+    try:
+        for i, s in enumerate(sims):
+            if i > 0:
+                s.peer_attach(0, sims[i - 1])
+            if i + 1 < len(sims):
+                s.peer_attach(1, sims[i + 1])
+        for s in sims:
+            s.comm_fused(FUSED_FLAGS)
+        n = dim ** 3
+        for rep in range(2):      # the second pass re-initialises without any host synchronisation in between
+            for s in sims:
+                s.init()
+            k = 0
+            done = 0
+            rho = np.full((1 + its // every, n), np.nan, dtype=sims[0].dtype)
+            u = np.full((1 + its // every, 3, n), np.nan, dtype=sims[0].dtype)
+            for s in sims:
+                s.read_macros(rho[k], u[k])
+            k += 1
+            while done < its:
+                chunk = min(every - done % every, its - done)
+                # deliberately unbalanced enqueue order: every slab gets its whole chunk at once
+                for s in (sims if rep == 0 else sims[::-1]):
+                    s.run(chunk, every)
+                done += chunk
+                if done % every == 0:
+                    for s in sims:
+                        s.read_macros(rho[k], u[k])
+                    k += 1
+            for s in sims:
+                s.sync()
+                assert s.launch_count == its          # ONE launch per iteration and slab
+            assert rho.tobytes() == exp["rho"].tobytes(), rep
+            assert u.tobytes() == exp["u"].tobytes(), rep
+    finally:
+        for s in sims:
+            s.sync()
+        for s in sims:
+            s.close()
+
+
+def test_neighbour_attachment_is_validated():
+    """lbm_peer_attach / lbm_ipc_attach refuse a neighbour that is not adjacent or runs another configuration
+    (a wrong blob would otherwise let a boundary kernel overwrite planes the other slab OWNS)."""
+    from lbmcl_b200.capi import FUSED_FLAGS, LbmError, Simulation
+    a = Simulation(dim=32, stride=32, z_range=(0, 8))
+    b = Simulation(dim=32, stride=32, z_range=(8, 16))
+    c = Simulation(dim=32, stride=32, z_range=(16, 32))
+    d = Simulation(dim=32, stride=8, z_range=(8, 16))
+    try:
+        with pytest.raises(LbmError, match="not adjacent"):
+            a.peer_attach(1, c)
+        with pytest.raises(LbmError, match="not adjacent"):
+            b.peer_attach(0, c)          # wrong face
+        with pytest.raises(LbmError, match="different configuration"):
+            a.peer_attach(1, d)
+        with pytest.raises(LbmError, match="cube boundary"):
+            a.peer_attach(0, b)
+        with pytest.raises(LbmError, match="no attached neighbour"):
+            b.comm_fused(FUSED_FLAGS)
+        a.peer_attach(1, b)
+        with pytest.raises(LbmError, match="already has a neighbour"):
+            a.peer_attach(1, b)
+        # the same checks through the IPC blob (exported and attached inside one process is refused by CUDA
+        # only at the open; the geometry checks come first)
+        blob = c.ipc_export()
+        with pytest.raises(LbmError, match="not adjacent"):
+            b.ipc_attach(0, blob)
+        # a slab with neighbours but no transport is not drivable on its own
+        a.init()
+        with pytest.raises(LbmError, match="peer neighbours"):
+            a.run(1, 0)
+        with pytest.raises(LbmError, match="peer neighbours"):
+            a.step(False)
+        t = a.launch_times_ms()          # the refused calls left no half-recorded event pair behind
+        assert len(t) == 0
+        a.ipc_detach()
+        a.run(2, 0)
+        assert len(a.launch_times_ms()) == 1
+    finally:
+        for s in (a, b, c, d):
+            s.close()
+
+
 def test_dense_halo_transport_matches_single():
     """The one-process-per-device transport (pack -> copy -> unpack), driven from the host the way
     bench.py drives it under torchrun, here with both slabs on device 0 and cudaMemcpy as the wire."""
@@ -340,6 +454,84 @@ def test_tma_variant_rows_segments_and_slabs(tx, precision, monkeypatch):
     with Group([0, 0, 0, 0], dim=64, precision=precision, stride=32, variant=16) as g:
         rho, u = g.run_snapshots(9, 3)
     assert rho.tobytes() == exp["rho"].tobytes() and u.tobytes() == exp["u"].tobytes()
+
+
+def test_group_dump_view_matches_the_single_device_view():
+    """lbm_group_read_f: the -f view gathered over z-slabs (the reference's storeF has no single-device
+    restriction, lbmcl.hpp:206-258)."""
+    from lbmcl_b200.capi import Group
+    dim, stride = 16, 16
+    for precision in ("f32", "f64"):
+        o = Oracle(precision)
+        st = o.alloc(dim)
+        o.init(st, dim, stride, 0.0089, 0.05)
+        with Group([0, 0, 0, 0], dim=dim, precision=precision, stride=stride) as g:
+            g.init()
+            for its in range(0, 5):
+                exp = st["f_stream"] if (its + 1) % 2 == 0 else st["f_collide"]
+                got = g.read_f()
+                assert np.array_equal(np.isnan(got), np.isnan(exp)), its
+                assert got.tobytes() == exp.tobytes(), its
+                g.run(1, 0)
+                o.step(st, dim, stride, 0.0089, 0.05, its + 1, 0)
+
+
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+def test_nvrtc_specialised_variant_is_bit_identical(precision):
+    """LBM_VARIANT_NVRTC: the step kernel compiled at run time with DIM / stride / offsets / INV_TAU / U as
+    literals (the reference's -D kernel options, lbmcl.hpp:131-156)."""
+    for dim, stride, nu, u_lid, its, every in ((32, 32, 0.0089, 0.05, 10, 1), (16, 2, 0.0123456789, -0.03, 6, 2),
+                                               (32, 1024, 0.02, 0.1, 7, 7), (16, 4096, 0.0089, 0.05, 7, 7)):
+        exp = Oracle(precision).run(dim, stride, nu, u_lid, its, every)
+        with _sim(dim=dim, precision=precision, viscosity=nu, velocity=u_lid, stride=stride, variant=32) as s:
+            rho, u = s.run_snapshots(its, every)
+        assert rho.tobytes() == exp["rho"].tobytes() and u.tobytes() == exp["u"].tobytes(), (dim, stride)
+    exp = Oracle(precision).run(32, 32, 0.0089, 0.05, 8, 4)
+    with _sim(dim=32, precision=precision, stride=32, variant=32, fast_math=True) as s:
+        rho, u = s.run_snapshots(8, 4)
+    _compare(rho, u, exp["rho"], exp["u"], 0.05, TOL[precision], exact=False)
+
+
+def test_tma_variant_inside_cuda_graphs():
+    """TMA-fed kernels replayed from the 16-iteration CUDA graphs of lbm_run (small lattices, long runs): the
+    shared-memory opt-in is set once per device at lbm_create, not inside the capture."""
+    dim, stride, its = 32, 32, 16 * 9 + 5
+    exp = Oracle("f32").run(dim, stride, 0.0089, 0.05, its, its)
+    with _sim(dim=dim, stride=stride, variant=16) as s:
+        s.init()
+        s.run(its, its)
+        rho, u = s.read_macros()
+        assert s.launch_count == its
+    assert rho.tobytes() == exp["rho"][1].tobytes() and u.tobytes() == exp["u"][1].tobytes()
+
+
+def test_async_read_back_overlaps_and_is_ordered():
+    """lbm_read_macros_async into page-locked memory: the copy sees exactly the state at the call, later
+    iterations run alongside, and the next flagged iteration waits for the copy before it overwrites rho/u."""
+    from lbmcl_b200.capi import pinned_array
+    dim, stride, every, its = 64, 32, 5, 20
+    exp = Oracle("f32").run(dim, stride, 0.0089, 0.05, its, every)
+    n = dim ** 3
+    bufs = [(pinned_array((n,), np.float32), pinned_array((3, n), np.float32)) for _ in range(2)]
+    with _sim(dim=dim, stride=stride) as s:
+        s.init()
+        k = 0
+        s.read_macros_async(*bufs[0])
+        got = []
+        for chunk in range(its // every):
+            s.run(every, every)                       # enqueued while the previous copy may still be running
+            s.read_wait()
+            got.append((bufs[k % 2][0].copy(), bufs[k % 2][1].copy()))
+            k += 1
+            s.read_macros_async(*bufs[k % 2])
+        s.read_wait()
+        got.append((bufs[k % 2][0].copy(), bufs[k % 2][1].copy()))
+        total, kernels = s.time_ms()
+        assert total >= kernels > 0
+    assert len(got) == 1 + its // every
+    for i, (r, v) in enumerate(got):
+        assert r.tobytes() == exp["rho"][i].tobytes(), i
+        assert v.tobytes() == exp["u"][i].tobytes(), i
 
 
 def test_per_launch_timings_like_the_reference_event_list():

@@ -1,8 +1,19 @@
 #!/usr/bin/env python3
-"""Run under torchrun: z-slab run over WORLD_SIZE GPUs (one process each, NCCL halo exchange, the
-same code path as bench.py) compared bit for bit with the oracle on rank 0.
+"""Run under torchrun: z-slab runs over WORLD_SIZE ranks (one process each; the same code path as bench.py)
+compared bit for bit with the CPU oracle on rank 0, for every transport of include/lbm_b200.h:
+
+    host     split-phase ABI, dense halos exchanged by the host through torch.distributed   (2a)
+    dense    library-owned NCCL communicator, dense halos                                    (2b)
+    flags    CUDA IPC peer stores + in-kernel epoch flags, one launch per iteration          (2c)
+    token    CUDA IPC peer stores + NCCL token                                               (2d)
+
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
-        --master-port 29511 tools/multi_gpu_check.py"""
+        --master-port 29511 tools/multi_gpu_check.py [--backend nccl|gloo] [--same-device] [--only flags]
+
+`--backend gloo --same-device` puts every rank on GPU 0 and bootstraps over gloo: only the NCCL-free
+transport ("flags") can run then -- the ranks' kernels are time-sliced on the one GPU and meet through the
+flag words; used by tests/test_gpu_multiproc.py on a one-GPU box.  Exit status 1 on any mismatch."""
+import argparse
 import os
 import sys
 
@@ -20,31 +31,52 @@ class DevBuf:
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (int(ptr), False), "version": 2}
 
 
+CASES = (("host", "f32", 32, 32, 10), ("host", "f64", 64, 32, 6),
+         ("dense", "f32", 32, 32, 10), ("dense", "f64", 64, 32, 7), ("dense", "f32", 128, 32, 20),
+         ("token", "f32", 32, 32, 10), ("token", "f64", 64, 32, 7), ("token", "f32", 128, 32, 21),
+         ("flags", "f32", 32, 32, 10), ("flags", "f64", 64, 32, 7), ("flags", "f32", 128, 32, 21),
+         ("flags", "f32", 64, 4096, 9),      # DIM < stride < cells: the row-base addressing on a slab
+         ("flags", "f64", 64, 1, 6))         # AoS
+
+
 def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--backend", default="nccl", choices=["nccl", "gloo"])
+    ap.add_argument("--same-device", action="store_true")
+    ap.add_argument("--only", default="")
+    a = ap.parse_args()
     rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    if a.same_device:
+        lr = 0
     torch.cuda.set_device(lr)
     dev = torch.device("cuda", lr)
-    dist.init_process_group("nccl", device_id=dev)
+    if a.backend == "nccl":
+        dist.init_process_group("nccl", device_id=dev)
+        where = dev
+    else:
+        dist.init_process_group("gloo")
+        where = torch.device("cpu")
     ok = True
-    for transport, precision, dim, stride, its in (("host", "f32", 32, 32, 10), ("host", "f64", 64, 32, 6),
-                                                   ("nccl-in-library", "f32", 32, 32, 10),
-                                                   ("nccl-in-library", "f64", 64, 32, 7),
-                                                   ("nccl-in-library", "f32", 128, 32, 20),
-                                                   ("fused", "f32", 32, 32, 10), ("fused", "f64", 64, 32, 7),
-                                                   ("fused", "f32", 128, 32, 21)):
+    for transport, precision, dim, stride, its in CASES:
+        if a.only and transport not in a.only.split(","):
+            continue
+        if a.backend == "gloo" and transport != "flags":
+            continue
+        if dim % world != 0 or dim // world < 1:
+            continue
         z0, z1 = slab_range(dim, world, rank)
         sim = Simulation(dim=dim, precision=precision, stride=stride, device=lr, z_range=(z0, z1))
         main_s = torch.cuda.Stream(device=dev)
         sim.set_stream(main_s.cuda_stream)
         has_lo, has_hi = rank > 0, rank < world - 1
-        ts = "<f4" if precision == "f32" else "<f8"
-        n_h = sim.halo_elems
-        send = [torch.as_tensor(DevBuf(sim.halo_send_ptr(f), n_h, ts), device=dev) if ok_ else None
-                for f, ok_ in ((0, has_lo), (1, has_hi))]
-        recv = [torch.as_tensor(DevBuf(sim.halo_recv_ptr(f), n_h, ts), device=dev) if ok_ else None
-                for f, ok_ in ((0, has_lo), (1, has_hi))]
-        sim.init()
         if transport == "host":
+            ts = "<f4" if precision == "f32" else "<f8"
+            n_h = sim.halo_elems
+            send = [torch.as_tensor(DevBuf(sim.halo_send_ptr(f), n_h, ts), device=dev) if ok_ else None
+                    for f, ok_ in ((0, has_lo), (1, has_hi))]
+            recv = [torch.as_tensor(DevBuf(sim.halo_recv_ptr(f), n_h, ts), device=dev) if ok_ else None
+                    for f, ok_ in ((0, has_lo), (1, has_hi))]
+            sim.init()
             # split-phase ABI, exchange posted by the host through torch.distributed
             with torch.cuda.stream(main_s):
                 for it in range(1, its + 1):
@@ -55,36 +87,33 @@ def main():
                         r.wait()
                     sim.halo_unpack()
         else:
-            # library-driven: NCCL communicator inside the context, overlapped schedule in lbm_run
-            used = connect_slabs(sim, rank, world, dev, fused=(transport == "fused"))
+            used = connect_slabs(sim, rank, world, dev, transport=transport)
             if rank == 0:
-                print(f"  transport requested {transport}: in use {used}")
+                print(f"  transport requested {transport}: in use {used}", flush=True)
+            sim.init()
             sim.run(its - 3, its)
-            sim.run(3, its)
-        n = dim ** 3
-        npd = np.float32 if precision == "f32" else np.float64
-        rho = np.full(n, np.nan, dtype=npd)
-        u = np.full((3, n), np.nan, dtype=npd)
-        sim.read_macros(rho, u)
-        sim.close()
-        td = torch.float32 if precision == "f32" else torch.float64
+            sim.step(False)        # the per-launch entry point goes through the same schedule
+            sim.run(2, its)
+        rho, u = sim.read_macros_slab()
+        sim.sync()
         # gather the slabs on rank 0 (NaN-safe: ship raw bits)
-        bits = torch.from_numpy(np.concatenate([rho, u.reshape(-1)]).view(np.uint8)).to(dev)
+        bits = torch.from_numpy(np.concatenate([rho, u.reshape(-1)]).view(np.uint8).copy()).to(where)
         out = [torch.empty_like(bits) for _ in range(world)] if rank == 0 else None
         dist.gather(bits, out, dst=0)
+        dist.barrier()             # nobody frees a lattice a neighbour may still be storing into
+        sim.close()
         if rank == 0:
             from oracle import Oracle
+            npd = np.float32 if precision == "f32" else np.float64
             exp = Oracle(precision).run(dim, stride, 0.0089, 0.05, its, its)
-            full_rho = np.full(n, np.nan, dtype=npd)
-            full_u = np.full((3, n), np.nan, dtype=npd)
-            for r in range(world):
-                a = out[r].cpu().numpy().view(npd)
-                a0, a1 = slab_range(dim, world, r)
-                sl = slice(a0 * dim * dim, a1 * dim * dim)
-                full_rho[sl] = a[:n][sl]
-                full_u[:, sl] = a[n:].reshape(3, n)[:, sl]
+            n_slab = (dim // world) * dim * dim
+            parts = [o.cpu().numpy().view(npd) for o in out]
+            full_rho = np.concatenate([p[:n_slab] for p in parts])
+            full_u = np.concatenate([p[n_slab:].reshape(3, n_slab) for p in parts], axis=1)
             same = full_rho.tobytes() == exp["rho"][1].tobytes() and full_u.tobytes() == exp["u"][1].tobytes()
-            print(f"multi_gpu_check [{transport}] {precision} {dim}^3 x{its} on {world} ranks: {'bit-identical' if same else 'MISMATCH'}")
+            print(f"multi_gpu_check [{transport}] {precision} {dim}^3 stride {stride} x{its} on {world} ranks"
+                  f"{' (one GPU, time-sliced)' if a.same_device else ''}: {'bit-identical' if same else 'MISMATCH'}",
+                  flush=True)
             ok = ok and same
     dist.barrier()
     dist.destroy_process_group()
