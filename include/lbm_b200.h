@@ -156,6 +156,12 @@ int lbm_read_f(lbm_ctx *ctx, void *f_host);
  * Synchronises the context. */
 int lbm_time_ms(lbm_ctx *ctx, double *total_ms, double *kernels_ms);
 
+/* Extends the profiled span to "now" on the context's stream: a host that overlaps its output work with the
+ * device (asynchronous read-back, file writing on other threads) calls it when that work is finished, so that
+ * total_ms covers it the way the reference's total covers its blocking reads and the VTI writing between
+ * them (first event start -> last event end, lbmcl.hpp:548-556). */
+int lbm_mark_end(lbm_ctx *ctx);
+
 /* The individual durations behind kernels_ms, in enqueue order: one entry per lbm_step() launch or per
  * lbm_run() batch -- the per-event list of kernelsTimingsMS() (lbmcl.hpp:580-593).  *count receives the
  * number of entries; at most `capacity` of them are copied to `out` (may be NULL).  Synchronises. */

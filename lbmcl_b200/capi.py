@@ -23,7 +23,7 @@ FUSED_OFF, FUSED_FLAGS, FUSED_TOKEN = 0, 1, 2
 EXPORTS = [
     "lbm_default_params", "lbm_create", "lbm_destroy", "lbm_last_error", "lbm_init", "lbm_step", "lbm_run",
     "lbm_sync", "lbm_read_macros", "lbm_read_macros_slab", "lbm_host_alloc", "lbm_host_free", "lbm_read_macros_async",
-    "lbm_read_wait", "lbm_read_map", "lbm_read_f", "lbm_time_ms", "lbm_launch_times_ms", "lbm_device_name",
+    "lbm_read_wait", "lbm_mark_end", "lbm_read_map", "lbm_read_f", "lbm_time_ms", "lbm_launch_times_ms", "lbm_device_name",
     "lbm_effective_params", "lbm_block_shape", "lbm_device_bytes", "lbm_spec_cubin", "lbm_launch_count", "lbm_iteration",
     "lbm_set_stream", "lbm_step_planes", "lbm_advance", "lbm_z_range", "lbm_halo_elems", "lbm_halo_send_buffer",
     "lbm_halo_recv_buffer", "lbm_halo_pack", "lbm_halo_unpack", "lbm_comm_unique_id", "lbm_comm_init", "lbm_ipc_export",
@@ -91,6 +91,7 @@ def load() -> ctypes.CDLL:
     lib.lbm_host_free.restype = None
     lib.lbm_read_macros_async.argtypes = [vp, vp, vp]
     lib.lbm_read_wait.argtypes = [vp]
+    lib.lbm_mark_end.argtypes = [vp]
     lib.lbm_spec_cubin.argtypes = [ctypes.POINTER(LbmParams), vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
     lib.lbm_read_map.argtypes = [vp, vp]
     lib.lbm_read_f.argtypes = [vp, vp]

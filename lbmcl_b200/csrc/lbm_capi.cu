@@ -1428,6 +1428,15 @@ int lbm_time_ms(lbm_ctx *c, double *total_ms, double *kernels_ms)
     return LBM_OK;
 }
 
+int lbm_mark_end(lbm_ctx *c)
+{
+    if (!c) return LBM_ERR_INVALID;
+    if (!c->initialised) return fail(c, LBM_ERR_STATE, "lbm_mark_end before lbm_init");
+    int rc = use_device(c);
+    if (rc != LBM_OK) return rc;
+    return record_last(c);
+}
+
 int lbm_launch_times_ms(lbm_ctx *c, double *out, int64_t capacity, int64_t *count)
 {
     if (!c || !count) return LBM_ERR_INVALID;

@@ -289,6 +289,28 @@ __device__ __forceinline__ void bounce_back(T (&f)[Q])
     });
 }
 
+// Gather load.  -DLBM_LD_NOALLOC (an A/B knob, profiles/r02_experiments.md): the e_x = 0 gathers, whose lines no
+// other warp touches, bypass L1 allocation (ld.global.L1::no_allocate).
+template <typename T, int EX>
+__device__ __forceinline__ T ld_gather(const T *p)
+{
+#ifdef LBM_LD_NOALLOC
+    if constexpr (EX == 0 && sizeof(T) == 4) {
+        float v;
+        asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+        return v;
+    } else if constexpr (EX == 0 && sizeof(T) == 8) {
+        double v;
+        asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+        return v;
+    } else {
+        return *p;
+    }
+#else
+    return *p;
+#endif
+}
+
 // ---- in-kernel slab ordering (PEER_FLAGS) ----
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p)
 {
@@ -402,7 +424,7 @@ __device__ __forceinline__ void step_pull_cells(const StepArgs<T> &a, const int 
                 f[q][0] = *(reinterpret_cast<const T *>(p + LBM_U_SOFF(T, a, q)) - ex(q));
             } else {
                 const char *p = ex(q) == 0 ? s0 : (ex(q) == 1 ? sm1 : sp1);
-                f[q][0] = *reinterpret_cast<const T *>(p + LBM_U_GOFF(T, a, q, LM));
+                f[q][0] = ld_gather<T, ex(q)>(reinterpret_cast<const T *>(p + LBM_U_GOFF(T, a, q, LM)));
             }
         });
     } else {
@@ -591,8 +613,8 @@ __device__ __forceinline__ void step_pull_body(const StepArgs<T> &a)
         // block-uniform (bz == 1): is this block part of a boundary plane that talks to a neighbour?
         const bool lo_face = a.peer_lo != nullptr && z == a.z_own_begin;
         const bool hi_face = a.peer_hi != nullptr && z == a.z_own_end - 1;
-        const bool first = threadIdx.x == 0 && threadIdx.y == 0;
         if (lo_face || hi_face) {
+            const bool first = threadIdx.x == 0 && threadIdx.y == 0;
             // the halo plane I gather from holds the neighbour's populations of the previous phase, and the
             // neighbour has finished reading the halo plane I am about to overwrite
             if (first) {
@@ -600,15 +622,17 @@ __device__ __forceinline__ void step_pull_body(const StepArgs<T> &a)
                 if (hi_face) slab_wait(a.sync.flag_in + 1, a.sync.wait_epoch, a.sync.timeout_ns, a.sync.error);
             }
             __syncthreads();
-        }
-        if (live) step_pull_cells<T, VEC, FAST, MACRO, PEER, LM>(a, x0, y, z, rowbits, mask);
-        if (lo_face || hi_face) {
+            if (live) step_pull_cells<T, VEC, FAST, MACRO, PEER_STORE, LM>(a, x0, y, z, rowbits, mask);
             __syncthreads();
             if (first) {
                 const unsigned n_blocks = gridDim.x * gridDim.y;
                 if (lo_face) slab_signal(a.sync.count + 0, n_blocks, a.sync.flag_out[0], a.sync.signal_epoch);
                 if (hi_face) slab_signal(a.sync.count + 1, n_blocks, a.sync.flag_out[1], a.sync.signal_epoch);
             }
+        } else {
+            // interior planes (all but two of the launch): exactly the code of the single-device kernel, so that
+            // the neighbour handling above costs them neither instructions nor registers
+            if (live) step_pull_cells<T, VEC, FAST, MACRO, PEER_NONE, LM>(a, x0, y, z, rowbits, mask);
         }
     } else {
         if (!live) return;
@@ -616,16 +640,29 @@ __device__ __forceinline__ void step_pull_body(const StepArgs<T> &a)
     }
 }
 
-// Occupancy: the fp32 one-cell-per-thread kernel needs 40 registers (6 blocks of 256 threads per SM).
-// The neighbour code of the PEER variants takes it to 48 (5 blocks); building with -DLBM_PEER_TIGHT caps
-// them at 40 as well, at the price of 16-40 bytes of spill (A/B-measured, see profiles/).
-#ifndef LBM_PEER_TIGHT
-#define LBM_PEER_TIGHT 0
+// Occupancy.  The step kernel is latency-bound as much as bandwidth-bound: its throughput follows the number
+// of resident warps (measured, profiles/r02_occupancy.md: the same code at 72 instead of 40 registers per
+// thread -- 3 instead of 6 blocks per SM -- runs 22 % slower), so the register budget is pinned per variant
+// instead of being left to ptxas' heuristics:
+//   fp32, 1 cell/thread     6 blocks of 256 threads per SM (40 registers; the kernel needs exactly that);
+//                           the PEER_FLAGS kernel too: only its two boundary planes run the neighbour code
+//                           and take the few spills it costs at 40 registers
+//   fp64, 1 cell/thread     3 blocks (<= 80 registers; needs 73)
+//   fp32, 2 cells/thread    3 blocks;  4 cells/thread and fp64 2 cells/thread: 1 block (117-134 registers)
+// (boundary-only launches -- PEER_STORE -- and launches with macro stores are rare: one block less.)
+#ifndef LBM_MINB_F32
+#define LBM_MINB_F32 6
+#endif
+#ifndef LBM_MINB_F64
+#define LBM_MINB_F64 3
 #endif
 template <typename T, int VEC, bool MACRO, int PEER>
 __host__ __device__ constexpr int step_min_blocks()
 {
-    return (sizeof(T) == 4 && VEC == 1 && !MACRO && (PEER == PEER_NONE || LBM_PEER_TIGHT)) ? 6 : 1;
+    constexpr bool rare = MACRO || PEER == PEER_STORE;
+    if (VEC == 1) return (sizeof(T) == 4 ? LBM_MINB_F32 : LBM_MINB_F64) - (rare ? 1 : 0);
+    if (VEC == 2 && sizeof(T) == 4) return 3;
+    return 1;
 }
 
 template <typename T, int VEC, bool FAST, bool MACRO, int PEER, int LM>

@@ -14,7 +14,11 @@
 //   * optional z-slab decomposition over several GPUs (`gpus` > 1);
 //   * device errors are reported as "file:line what(code) - cudaErrorName" by the library and end the
 //     program with a non-zero status here (reference CLUtil.hpp:101-117 does the same with CL names);
-//   * the ASCII VTI body is formatted by several host threads (identical bytes, less wall time).
+//   * output is pipelined (the reference blocks in storeData, lbmcl.hpp:261-334): rho/u are
+//     read back asynchronously into one of two page-locked buffers on a copy stream while the device already
+//     computes the next `every` iterations, and a writer thread formats and writes the VTI file meanwhile;
+//     the ASCII body is formatted by several threads with an exact "%.16e" routine (fmt_e16.hpp) -- the bytes
+//     are the reference's, the wall time is not.
 #pragma once
 
 #include <cmath>
@@ -31,6 +35,7 @@
 #include <vector>
 
 #include "../../include/lbm_b200.h"
+#include "fmt_e16.hpp"
 
 #define LBM_INITIALIZE_KERNEL_NAME "initialize"
 #define LBM_COMPUTE_KERNEL_NAME "compute"
@@ -61,8 +66,15 @@ class LBMCL {
     std::string device_name = "?";
     int64_t device_bytes = 0;
 
-    std::vector<T> rho_values, u_values, f_values;
+    std::vector<T> f_values;
     std::vector<int32_t> map_values;
+
+    // snapshot pipeline: two host buffers (page-locked when possible), one writer thread at a time
+    T *rho_buf[2] = {nullptr, nullptr};
+    T *u_buf[2] = {nullptr, nullptr};
+    bool buf_pinned = false;
+    std::thread writer;
+    size_t n_snapshots = 0;
 
     static constexpr size_t Q = 19, D = 3;
 
@@ -117,11 +129,8 @@ class LBMCL {
         return s.str();
     }
 
-    void readMacros()
-    {
-        if (group) check(lbm_group_read_macros(group, rho_values.data(), u_values.data()), "read_rho/read_u");
-        else check(lbm_read_macros(ctx, rho_values.data(), u_values.data()), "read_rho/read_u");
-    }
+    int n_ctx() const { return group ? lbm_group_size(group) : 1; }
+    lbm_ctx *ctx_at(int i) const { return group ? lbm_group_ctx(group, i) : ctx; }
 
     // map.dump, lbmcl.hpp:159-203.  A missing directory is a silent no-op there (no check on the
     // ofstream) and here.
@@ -160,7 +169,8 @@ class LBMCL {
     // f_<it>.dump, lbmcl.hpp:206-258: the populations iteration `it` reads, CSoA order.
     void storeF(size_t iteration)
     {
-        check(lbm_read_f(ctx, f_values.data()), "read_f");
+        if (group) check(lbm_group_read_f(group, f_values.data()), "read_f");
+        else check(lbm_read_f(ctx, f_values.data()), "read_f");
         FILE *fp = std::fopen(numbered(dump_path, "f_", iteration, ".dump").c_str(), "w");
         if (!fp) return;
         const int dd = (int)digits(dim);
@@ -196,21 +206,72 @@ class LBMCL {
         std::fclose(fp);
     }
 
-    // "%.16e " exactly as operator<< with std::scientific and precision 16 prints it
-    static void put(std::string &out, T v)
+    // ---- VTI output, lbmcl.hpp:261-334: rho then 3-component v over the wet cube, x fastest ----
+
+    // one z-plane of one array as text; every value is "%.16e " exactly as operator<< with std::scientific and
+    // precision 16 prints it
+    void formatPlane(std::string &out, int pass, size_t z, const T *rho, const T *u) const
     {
-        char buf[40];
-        const int n = std::snprintf(buf, sizeof buf, "%.16e ", (double)v);
-        out.append(buf, (size_t)n);
+        const size_t from = 1, to = dim - 1, n = cells();
+        out.clear();
+        out.reserve((to - from) * (to - from) * (pass == 0 ? 25 : 75) + dim);
+        char tmp[3 * 32];
+        for (size_t y = from; y < to; ++y) {
+            for (size_t x = from; x < to; ++x) {
+                const size_t id = x + y * dim + z * dim * dim;
+                int len = 0;
+                if (pass == 0) {
+                    len = lbm_fmt::fmt_e16((double)rho[id], tmp);
+                    tmp[len++] = ' ';
+                } else {
+                    for (size_t c = 0; c < 3; ++c) {
+                        len += lbm_fmt::fmt_e16((double)u[c * n + id], tmp + len);
+                        tmp[len++] = ' ';
+                    }
+                }
+                out.append(tmp, (size_t)len);
+            }
+            out += '\n';
+        }
     }
 
-    // lbmcl.<it>.vti, lbmcl.hpp:261-334: rho then 3-component v over the wet cube, x fastest.
-    void storeData(size_t iteration)
+    // Formats the planes of one array in batches of `nthreads` planes: while batch b is written, batch b+1 is
+    // being formatted, so that formatting and file I/O overlap and the text never exists in memory as a whole.
+    void writeArray(FILE *fp, int pass, const T *rho, const T *u, unsigned nthreads) const
     {
-        readMacros();
+        const size_t planes = dim - 2;
+        const size_t per = nthreads;
+        const size_t n_batches = (planes + per - 1) / per;
+        std::vector<std::string> text[2];
+        text[0].resize(per);
+        text[1].resize(per);
+        auto format_batch = [&](size_t b, std::vector<std::string> &out) {
+            auto work = [&](size_t j) {
+                const size_t k = b * per + j;
+                if (k < planes) formatPlane(out[j], pass, 1 + k, rho, u);
+                else out[j].clear();
+            };
+            std::vector<std::thread> pool;
+            for (size_t j = 1; j < per; ++j) pool.emplace_back(work, j);
+            work(0);
+            for (auto &t : pool) t.join();
+        };
+        format_batch(0, text[0]);
+        for (size_t b = 0; b < n_batches; ++b) {
+            std::thread next;
+            if (b + 1 < n_batches) next = std::thread(format_batch, b + 1, std::ref(text[(b + 1) & 1]));
+            for (const std::string &c : text[b & 1]) std::fwrite(c.data(), 1, c.size(), fp);
+            if (next.joinable()) next.join();
+        }
+    }
+
+    void writeVTI(size_t iteration, const T *rho, const T *u) const
+    {
         FILE *fp = std::fopen(numbered(vtk_path, "lbmcl.", iteration, ".vti").c_str(), "w");
-        if (!fp) return;
-        const size_t from = 1, to = dim - 1, extent = to - from - 1, n = cells();
+        if (!fp) return;  // a missing directory is a silent no-op in the reference (no check on the ofstream)
+        std::vector<char> iobuf(8u << 20);
+        std::setvbuf(fp, iobuf.data(), _IOFBF, iobuf.size());
+        const size_t extent = dim - 3;
         const char *type = std::is_same<T, float>::value ? "Float32" : "Float64";
         std::fprintf(fp,
                      "<?xml version=\"1.0\"?>\n"
@@ -220,49 +281,39 @@ class LBMCL {
                      "      <PointData Scalars=\"rho\">\n"
                      "        <DataArray type=\"%s\" Name=\"rho\" NumberOfComponents=\"1\" format=\"ascii\">\n",
                      extent, extent, extent, extent, extent, extent, type);
-
-        // format z-planes in parallel, write them in order
-        const size_t planes = to - from;
         unsigned nthreads = std::thread::hardware_concurrency();
         if (nthreads == 0) nthreads = 1;
         if (nthreads > 32) nthreads = 32;
-        if (nthreads > planes) nthreads = (unsigned)planes;
-        if (nthreads == 0) nthreads = 1;
-        for (int pass = 0; pass < 2; ++pass) {
-            std::vector<std::string> chunk(planes);
-            auto work = [&](unsigned tid) {
-                for (size_t k = tid; k < planes; k += nthreads) {
-                    const size_t z = from + k;
-                    std::string &out = chunk[k];
-                    out.reserve((to - from) * (to - from) * (pass == 0 ? 24 : 72) + 64);
-                    for (size_t y = from; y < to; ++y) {
-                        for (size_t x = from; x < to; ++x) {
-                            const size_t id = x + y * dim + z * dim * dim;
-                            if (pass == 0) {
-                                put(out, rho_values[id]);
-                            } else {
-                                put(out, u_values[0 * n + id]);
-                                put(out, u_values[1 * n + id]);
-                                put(out, u_values[2 * n + id]);
-                            }
-                        }
-                        out += '\n';
-                    }
-                }
-            };
-            std::vector<std::thread> pool;
-            for (unsigned t = 1; t < nthreads; ++t) pool.emplace_back(work, t);
-            work(0);
-            for (auto &t : pool) t.join();
-            for (const std::string &c : chunk) std::fwrite(c.data(), 1, c.size(), fp);
-            if (pass == 0)
-                std::fprintf(fp,
-                             "        </DataArray>\n"
-                             "        <DataArray type=\"%s\" Name=\"v\" NumberOfComponents=\"3\" format=\"ascii\">\n",
-                             type);
-        }
+        if (nthreads > dim - 2) nthreads = (unsigned)(dim - 2);
+        writeArray(fp, 0, rho, u, nthreads);
+        std::fprintf(fp,
+                     "        </DataArray>\n"
+                     "        <DataArray type=\"%s\" Name=\"v\" NumberOfComponents=\"3\" format=\"ascii\">\n",
+                     type);
+        writeArray(fp, 1, rho, u, nthreads);
         std::fputs("        </DataArray>\n      </PointData>\n    </Piece>\n  </ImageData>\n</VTKFile>\n", fp);
         std::fclose(fp);
+    }
+
+    // The reference's storeData(it) (blocking reads + file, lbmcl.hpp:261-334) as a pipeline stage.  Called
+    // right after the iterations up to `iteration` have been enqueued; `enqueue_more` enqueues the work that may
+    // overlap with this snapshot's read-back and file (the next batch of iterations), or is empty.
+    template <typename F>
+    void storeData(size_t iteration, F enqueue_more)
+    {
+        const size_t slot = n_snapshots & 1;  // its previous user (snapshot n-2) was joined before snapshot n-1 started
+        for (int i = 0; i < n_ctx(); ++i)     // every slab copies its own planes into the global arrays
+            check(lbm_read_macros_async(ctx_at(i), rho_buf[slot], u_buf[slot]), "read_rho/read_u");
+        enqueue_more();                        // the device carries on while the copy runs
+        for (int i = 0; i < n_ctx(); ++i) check(lbm_read_wait(ctx_at(i)), "read_rho/read_u");
+        if (writer.joinable()) writer.join();  // one file at a time, in order
+        const T *r = rho_buf[slot], *v = u_buf[slot];
+        writer = std::thread([this, iteration, r, v] { writeVTI(iteration, r, v); });
+        ++n_snapshots;
+    }
+    void storeData(size_t iteration)
+    {
+        storeData(iteration, [] {});
     }
 
 public:
@@ -295,6 +346,16 @@ public:
 
     ~LBMCL()
     {
+        if (writer.joinable()) writer.join();
+        for (int i = 0; i < 2; ++i) {
+            if (buf_pinned) {
+                lbm_host_free(rho_buf[i]);
+                lbm_host_free(u_buf[i]);
+            } else {
+                delete[] rho_buf[i];
+                delete[] u_buf[i];
+            }
+        }
         if (group) lbm_group_destroy(group);
         if (ctx) lbm_destroy(ctx);
     }
@@ -316,6 +377,8 @@ public:
         p.device = deviceID < 0 ? 0 : deviceID;
         p.variant = aa ? LBM_VARIANT_AA : LBM_VARIANT_AUTO;
         if (const char *v = std::getenv("LBM_VARIANT")) p.variant = std::atoi(v);
+        // -w is a hint by default; LBM_EXACT_BLOCK=1 makes the library honour it (block-shape sweeps)
+        if (const char *v = std::getenv("LBM_EXACT_BLOCK")) p.reserved[1] = std::atoi(v) == 1 ? 1 : 0;
         char name[256] = "?";
         if (gpus > 1) {
             std::vector<int32_t> devs;
@@ -337,55 +400,86 @@ public:
             device_bytes = lbm_device_bytes(ctx);
         }
         device_name = name;
-        if (dump_f && gpus > 1) {
-            std::cerr << "-f (dump_f) needs the whole cube on one device; run without --gpus" << std::endl;
-            std::exit(1);
-        }
         if (dump_map) map_values.resize(cells());
         if (dump_f) f_values.resize(cells() * Q);
         if (dump_data) {
-            rho_values.resize(cells());
-            u_values.resize(cells() * D);
+            // two snapshot buffers, page-locked so that the read-back is a real asynchronous DMA
+            void *p[4] = {nullptr, nullptr, nullptr, nullptr};
+            bool ok = true;
+            for (int i = 0; i < 4 && ok; ++i)
+                ok = lbm_host_alloc((i < 2 ? cells() : cells() * D) * sizeof(T), &p[i]) == LBM_OK;
+            if (ok) {
+                buf_pinned = true;
+                for (int i = 0; i < 2; ++i) {
+                    rho_buf[i] = static_cast<T *>(p[i]);
+                    u_buf[i] = static_cast<T *>(p[2 + i]);
+                }
+            } else {  // pageable memory works too (the copies then block a little longer)
+                for (int i = 0; i < 4; ++i) lbm_host_free(p[i]);
+                for (int i = 0; i < 2; ++i) {
+                    rho_buf[i] = new T[cells()];
+                    u_buf[i] = new T[cells() * D];
+                }
+            }
         }
     }
 
-    // lbmcl.hpp:485-521.  Kernel launches are asynchronous; the store* calls block like the reference's
-    // blocking enqueueReadBuffer calls do.
+    // lbmcl.hpp:485-521.  Kernel launches are asynchronous.  storeMap / storeF block like the reference's blocking
+    // enqueueReadBuffer calls do; storeData is pipelined: while snapshot k is copied, formatted and written, the
+    // device computes the iterations up to snapshot k+1.
     void performSimulation()
     {
         if (group) check(lbm_group_init(group), LBM_INITIALIZE_KERNEL_NAME);
         else check(lbm_init(ctx), LBM_INITIALIZE_KERNEL_NAME);
         if (dump_map) storeMap();
-        if (dump_data) storeData(0);
-        if (dump_f) storeF(0);
-
-        size_t it = 0;
-        while (it < iterations) {
-            if (dump_f) {
-                // f_<it+1>.dump holds what iteration it+1 reads (lbmcl.hpp:517-519): fetch it before the launch
-                storeF(it + 1);
-                check(lbm_step(ctx, (dump_data && ((it + 1) % every == 0)) ? 1 : 0), LBM_COMPUTE_KERNEL_NAME);
-                ++it;
-            } else {
-                // run up to the next iteration that stores data in one asynchronous batch
-                size_t chunk = iterations - it;
-                if (dump_data) {
-                    const size_t to_next = every - (it % every);
-                    if (to_next < chunk) chunk = to_next;
-                }
-                const int ev = dump_data ? (int)every : 0;
-                if (group) check(lbm_group_run(group, (int)chunk, ev), LBM_COMPUTE_KERNEL_NAME);
-                else check(lbm_run(ctx, (int)chunk, ev), LBM_COMPUTE_KERNEL_NAME);
-                it += chunk;
+        if (dump_f) {
+            // -f: one launch per iteration, the lattice is fetched before each (lbmcl.hpp:503, 517-519)
+            if (dump_data) storeData(0);
+            storeF(0);
+            for (size_t it = 1; it <= iterations; ++it) {
+                storeF(it);  // f_<it>.dump holds what iteration `it` reads
+                const int flag = (dump_data && it % every == 0) ? 1 : 0;
+                if (group) check(lbm_group_run(group, 1, flag), LBM_COMPUTE_KERNEL_NAME);
+                else check(lbm_step(ctx, flag), LBM_COMPUTE_KERNEL_NAME);
+                if (flag) storeData(it);
             }
-            if (dump_data && it % every == 0) storeData(it);
+            return;
+        }
+        // batches of iterations up to the next one that stores data, each enqueued as soon as the previous
+        // snapshot's copy has been queued
+        size_t it = 0;
+        auto run_batch = [&]() {
+            if (it >= iterations) return;
+            size_t chunk = iterations - it;
+            if (dump_data) {
+                const size_t to_next = every - (it % every);
+                if (to_next < chunk) chunk = to_next;
+            }
+            const int ev = dump_data ? (int)every : 0;
+            if (group) check(lbm_group_run(group, (int)chunk, ev), LBM_COMPUTE_KERNEL_NAME);
+            else check(lbm_run(ctx, (int)chunk, ev), LBM_COMPUTE_KERNEL_NAME);
+            it += chunk;
+        };
+        if (dump_data) {
+            storeData(0, run_batch);  // lbmcl.hpp:502; the first batch is enqueued behind the copy
+            while (it > 0 && it % every == 0) {
+                const size_t at = it;
+                storeData(at, run_batch);  // lbmcl.hpp:513-515
+                if (at >= iterations) break;
+            }
+        } else {
+            run_batch();
         }
     }
 
     void waitCompletion()  // lbmcl.hpp:525-532
     {
+        if (writer.joinable()) writer.join();
         if (group) check(lbm_group_sync(group), "finish");
         else check(lbm_sync(ctx), "finish");
+        // "Total time" spans the output work like the reference's does (lbmcl.hpp:548-556)
+        if (dump_data)
+            for (int i = 0; i < n_ctx(); ++i) check(lbm_mark_end(ctx_at(i)), "finish");
     }
 
     void performSimulationAndWait()

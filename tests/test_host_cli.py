@@ -69,8 +69,15 @@ def test_make_test8(tmp_path):
     VTI value with the oracle."""
     from oracle import Oracle
     res = str(tmp_path)
+    # the reference's default is OPTIMIZE=true (-o, reference Makefile:20): the target must pass as shipped ...
     r = subprocess.run(["make", "-C", HOST, "test8", f"RESULTS={res}", f"DUMP_PATH={res}"], stdout=subprocess.PIPE,
                        stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "verify: PASS (11 iterations compared)" in r.stdout
+    assert [l for l in r.stderr.splitlines() if l.count(";") == 11][0].split(";")[7] == "1"
+    # ... and with the strict kernels every value equals the oracle's
+    r = subprocess.run(["make", "-C", HOST, "test8", f"RESULTS={res}", f"DUMP_PATH={res}", "OPTIMIZE=false"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "verify: PASS (11 iterations compared)" in r.stdout
     for key in ("kernel options   = -DDIM=8 -DLWS=8 -DSTRIDE_DIV=3 -DSTRIDE_MOD=7 -DVISCOSITY=0.0089 -DVELOCITY=0.05 "
@@ -219,6 +226,49 @@ def test_gpus_flag(tmp_path):
     assert d["arrays"]["rho"].tobytes() == np.ascontiguousarray(wet(exp["rho"][1], 32)).tobytes()
 
 
+@pytest.mark.gpu
+def test_pipelined_snapshots_match_the_oracle(tmp_path):
+    """-e N with the asynchronous read-back / writer-thread pipeline: every file holds the state of ITS iteration
+    (the device runs ahead while a snapshot is copied and written), also when the run ends between snapshots."""
+    from oracle import Oracle
+    for precision, flag, its, every in (("f32", [], 23, 4), ("f64", ["-F"], 12, 3), ("f32", ["-A"], 9, 2)):
+        res = str(tmp_path / f"{precision}_{its}_{every}_{len(flag)}")
+        os.makedirs(res)
+        r = _run("-D", "0", "-d", "32", "-i", str(its), "-e", str(every), "-s", "32", "-v", res, "-p", res, *flag)
+        assert r.returncode == 0, r.stderr
+        exp = Oracle(precision).run(32, 32, 0.0089, 0.05, its, every)
+        files = sorted(f for f in os.listdir(res) if f.endswith(".vti"))
+        assert len(files) == 1 + its // every
+        for k, d in enumerate(_read_all(res, its, every)):
+            assert d["arrays"]["rho"].tobytes() == np.ascontiguousarray(wet(exp["rho"][k], 32)).tobytes(), (precision, k)
+            v = np.moveaxis(wet(exp["u"][k], 32), 0, -1).reshape(-1, 3)
+            assert d["arrays"]["v"].tobytes() == np.ascontiguousarray(v).tobytes(), (precision, k)
+        total = float(r.stdout.split("Total time:")[1].split("ms")[0])
+        kernels = float(r.stdout.split("Kernels time:")[1].split("ms")[0])
+        assert total >= kernels > 0
+
+
+@pytest.mark.gpu
+def test_dump_f_over_slabs(tmp_path):
+    """-f -G N (the reference's storeF has no device restriction, lbmcl.hpp:206-258)."""
+    import torch
+    from oracle import Oracle
+    if torch.cuda.device_count() < 2:
+        pytest.skip("-G N addresses devices D..D+N-1; one GPU only (lbm_group_read_f is covered in test_gpu_parity)")
+    dim, stride, its = 8, 8, 3
+    res = str(tmp_path)
+    r = _run("-D", "0", "-d", str(dim), "-i", str(its), "-e", "1", "-s", str(stride), "-v", res, "-p", res, "-f", "-G", "2")
+    assert r.returncode == 0, r.stderr
+    o = Oracle("f32")
+    st = o.alloc(dim)
+    o.init(st, dim, stride, 0.0089, 0.05)
+    for it in range(0, its + 1):
+        src = st["f_collide"] if it == 0 or it % 2 == 1 else st["f_stream"]
+        assert open(os.path.join(res, f"f_{it}.dump")).read() == _expected_f_dump(src, dim, stride), it
+        if it >= 1:
+            o.step(st, dim, stride, 0.0089, 0.05, it, 1)
+
+
 def test_benchmark_aggregation_drops_fastest_and_slowest(tmp_path):
     """benchmark.sh's aggregation (reference benchmark.sh:109-176): per configuration drop the runs
     with the smallest and the largest total time, average the rest."""
@@ -236,3 +286,16 @@ def test_benchmark_aggregation_drops_fastest_and_slowest(tmp_path):
     assert abs(float(f[9]) - 20.0) < 1e-9 and abs(float(f[10]) - 19.0) < 1e-9          # mean of 20, 22, 18
     g = out[2].split(";")
     assert g[2] == "128" and g[8] == "1" and float(g[9]) == 5.0
+    # roofline columns: kernelsMLUPS x 152 B / peak
+    assert len(f) == 15 and abs(float(f[13]) - float(f[12]) * 152 / 1000) < 1e-3 * float(f[13])
+    assert abs(float(f[14]) - float(f[13]) / 6550.7) < 1e-3
+    # the reference's own benchmark.csv format (benchmark.sh:109-176): key = device;precision;dim;lws;stride,
+    # no header, 9 columns -- runs that differ only in iterations / every / optimize merge
+    rows.append("NVIDIA B200;single;64;999;5;008,008,008;32;0;21.0;20.0;47.0;50.0")
+    stats.write_text("\n".join(rows) + "\n")
+    ref = subprocess.run(["awk", "-F;", "-v", "mode=reference", "-f", os.path.join(HOST, "aggregate.awk"), str(stats)],
+                         stdout=subprocess.PIPE, text=True, check=True).stdout.splitlines()
+    assert len(ref) == 2
+    r0 = ref[0].split(";")
+    assert r0[:5] == ["NVIDIA B200", "single", "64", "008,008,008", "32"] and len(r0) == 9
+    assert abs(float(r0[5]) - (20.0 + 22.0 + 18.0 + 21.0) / 4) < 1e-9      # 10 and 30 dropped, the merged run counted
