@@ -135,6 +135,9 @@ StepArgs<T> make_step_args(lbm_ctx *c, const Planes &pl, int peer_mode, const Co
     a.z_end = pl.z_end;
     a.n_local = c->n_local;
     a.lay = c->lay;
+    a.row_shift = c->lay.sdiv > ilog2(c->dim) ? c->lay.sdiv - ilog2(c->dim) : 0;
+    a.row_mask = (1 << a.row_shift) - 1;
+    a.blk18 = 18ll * c->lay.qpitch() * (long long)sizeof(T);
     a.c = k;
     for (int i = 0; i < 2; ++i)
         for (int q = 0; q < Q; ++q) a.stale[i][q] = stale[i][q];
@@ -144,7 +147,7 @@ StepArgs<T> make_step_args(lbm_ctx *c, const Planes &pl, int peer_mode, const Co
         a.soff[q] = q * S * es;
         const long long dcell = (long long)ey(q) * dim + (long long)ez(q) * plane;  // cells between the two rows
         const long long rowmul = lm == LM_ROWS ? Q : 1;                             // CSoA rows hold Q values per cell
-        if (lm == LM_GENERIC || lm == LM_BLOCKROWS) {
+        if (lm == LM_GENERIC) {
             a.goff[q] = a.poff[q] = 0;
         } else if (c->aa) {
             a.goff[q] = (opp(q) * S - rowmul * dcell) * es;  // SHIFT step: read (c - e_q, opp(q))
@@ -592,7 +595,8 @@ static int setup_tma(lbm_ctx *c, int n_sm)
     const size_t stage = (size_t)Q * c->tma_tx * c->esize;
     int ns = 2;
     int ctas = (int)((200 * 1024) / (2 * stage + 1024));
-    if (ctas > 5) ctas = 5;
+    const int by_registers = c->p.precision == LBM_F32 ? 4 : 2;  // the kernels' __launch_bounds__ (lbm_tma.cuh)
+    if (ctas > by_registers) ctas = by_registers;
     if (const char *e = std::getenv("LBM_TMA_NS")) ns = std::atoi(e);
     if (const char *e = std::getenv("LBM_TMA_CTAS")) ctas = std::atoi(e);
     if (ns < 2) ns = 2;

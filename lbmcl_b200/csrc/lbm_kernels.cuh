@@ -74,10 +74,15 @@ struct StepArgs {
     int z_begin, z_end;
     long long n_local;          // cells in local storage (pitch of the u components)
     Layout lay;
+    // LM_BLOCKROWS (DIM < stride): a CSoA block holds 2^row_shift whole x-rows
+    int row_shift, row_mask;    // log2(stride / DIM), stride / DIM - 1
+    long long blk18;            // 18 * stride * sizeof(T): what crossing into the next CSoA block adds to an address
     Consts<T> c;
     T stale[2][Q];              // [0]: w_q (rest equilibrium); [1]: f_eq_q(1, (U,0,0)); see header
     // Byte offsets precomputed by the host (uniform; they live in the constant bank):
-    //   goff[q]  LM_ROWS / LM_SOA: from the address of (x, y, z, 0) to the address of (x, y - ey, z - ez, q)
+    //   goff[q]  LM_ROWS / LM_SOA: from the address of (x, y, z, 0) to the address of (x, y - ey, z - ez, q);
+    //            LM_BLOCKROWS: the same as LM_SOA, valid while the source row lies in the same CSoA block --
+    //            every block boundary crossed on the way adds blk18
     //   soff[q]  from the address of (x, y, z, 0) to the address of (x, y, z, q)      ( = q * stride * sizeof(T) )
     long long goff[Q];
     long long soff[Q];
@@ -91,9 +96,10 @@ struct StepArgs {
 //   LM_ROWS       stride <= DIM: every x-row starts a CSoA block, so a shift in y or z is a constant
 //                 address offset and only the x position inside the row needs the block arithmetic;
 //   LM_SOA        stride >= number of stored cells: one block, every neighbour is a constant offset;
-//   LM_BLOCKROWS  DIM < stride < stored cells: a whole x-row lies inside one CSoA block, so the thread
-//                 forms the 9 row bases (one per (e_y, e_z)) once; direction q is then base + q*stride and
-//                 the x shift is +-1 element;
+//   LM_BLOCKROWS  DIM < stride < stored cells: a CSoA block holds stride/DIM whole x-rows, so the address of a
+//                 neighbour row is the SOA-style constant offset plus 18*stride elements per block boundary
+//                 crossed: the thread forms one full base and 8 small block-crossing counts (one per
+//                 (e_y, e_z)) instead of a CSoA index per access; the x shift is +-1 element;
 //   LM_GENERIC    full CSoA index computation per access (any stride; kept as a cross-check, test hook).
 enum : int { LM_GENERIC = 0, LM_ROWS = 1, LM_SOA = 2, LM_BLOCKROWS = 3 };
 
@@ -110,6 +116,9 @@ enum : int { PEER_NONE = 0, PEER_STORE = 1, PEER_FLAGS = 2 };
 #ifdef LBM_SPEC_DIM
 #define LBM_U_DIM(a) (LBM_SPEC_DIM)
 #define LBM_U_LAY(a) (Layout{LBM_SPEC_SDIV, (long long)(LBM_SPEC_STRIDE) - 1})
+#define LBM_U_ROWSHIFT(a) (LBM_SPEC_ROWSHIFT)
+#define LBM_U_ROWMASK(a) ((1 << (LBM_SPEC_ROWSHIFT)) - 1)
+#define LBM_U_BLK18(T, a) (18ll * (LBM_SPEC_STRIDE) * (long long)sizeof(T))
 #define LBM_U_ZS0(a) (0)
 #define LBM_U_NLOCAL(a) ((long long)(LBM_SPEC_DIM) * (LBM_SPEC_DIM) * (LBM_SPEC_DIM))
 #define LBM_U_CONSTS(T, a) (Consts<T>{T(LBM_SPEC_U_LID), T(LBM_SPEC_INV_TAU), {T(1.0) / T(3.0), T(1.0) / T(18.0), T(1.0) / T(36.0)}})
@@ -122,6 +131,9 @@ enum : int { PEER_NONE = 0, PEER_STORE = 1, PEER_FLAGS = 2 };
 #else
 #define LBM_U_DIM(a) ((a).dim)
 #define LBM_U_LAY(a) ((a).lay)
+#define LBM_U_ROWSHIFT(a) ((a).row_shift)
+#define LBM_U_ROWMASK(a) ((a).row_mask)
+#define LBM_U_BLK18(T, a) ((a).blk18)
 #define LBM_U_ZS0(a) ((a).zs0)
 #define LBM_U_NLOCAL(a) ((a).n_local)
 #define LBM_U_CONSTS(T, a) ((a).c)
@@ -377,11 +389,12 @@ __device__ __forceinline__ void step_pull_cells(const StepArgs<T> &a, const int 
     // ---- addresses: per-thread bases, per-direction offsets are uniform ----
     // LM_ROWS / LM_SOA: b0 = element index of (x0, y, z, q = 0); bm / bp = of (x0 - 1, ..) and (x0 + VEC, ..),
     // clamped into the row (the clamped values are only ever consumed by WALL cells).
-    // LM_BLOCKROWS: rb[(ey+1)*3 + ez+1] = element index of (x0, y - ey, z - ez, q = 0); the x +- 1 neighbours
-    // are the adjacent elements (a row never leaves its CSoA block; reading one element past either end
-    // of a row stays inside the allocation and is only consumed by WALL cells).
+    // LM_BLOCKROWS: one full base b0; nbc[(ey+1)*3 + ez+1] = byte correction for the CSoA block boundaries between
+    // row (y, z) and row (y - ey, z - ez): (blocks crossed) * blk18.  The x +- 1 neighbours are the adjacent
+    // elements (a row never leaves its CSoA block; reading one element past either end of a row stays inside
+    // the allocation and is only consumed by WALL cells).
     long long b0, bm = 0, bp = 0;
-    long long rb[9];
+    long long nbc[9];
     if constexpr (LM == LM_ROWS) {
         const long long rowbase = rowid * Q;
         const int xm = x0 > 0 ? x0 - 1 : 0;
@@ -395,12 +408,15 @@ __device__ __forceinline__ void step_pull_cells(const StepArgs<T> &a, const int 
         bm = id0 - 1;  // live rows have y >= 1, so id0 >= DIM
         bp = id0 + VEC;
     } else if constexpr (LM == LM_BLOCKROWS) {
+        b0 = lay.base(rowid) + x0;
+        const int rsh = LBM_U_ROWSHIFT(a);
+        const int r = (y + zl * dim) & LBM_U_ROWMASK(a);  // row inside its CSoA block
+        const long long blk18 = LBM_U_BLK18(T, a);
 #pragma unroll
         for (int dy = -1; dy <= 1; ++dy)
 #pragma unroll
             for (int dz = -1; dz <= 1; ++dz)
-                rb[(dy + 1) * 3 + dz + 1] = lay.base(rowid - (long long)dy * dim - (long long)dz * plane) + x0;
-        b0 = rb[4];
+                nbc[(dy + 1) * 3 + dz + 1] = (long long)((r - dy - dz * dim) >> rsh) * blk18;  // arithmetic shift: floor
     } else {
         b0 = lay.base(id0);
     }
@@ -409,7 +425,7 @@ __device__ __forceinline__ void step_pull_cells(const StepArgs<T> &a, const int 
     const char *const sp1 = reinterpret_cast<const char *>(a.src + bp);
     (void)sm1;
     (void)sp1;
-    (void)rb;
+    (void)nbc;
 
     // ---- gather: f[q][j] = G(x0 + j - ex, y - ey, z - ez, q) ----
     T f[Q][VEC];
@@ -420,8 +436,8 @@ __device__ __forceinline__ void step_pull_cells(const StepArgs<T> &a, const int 
                 const long long sid = id0 - ex(q) - (long long)ey(q) * dim - (long long)ez(q) * plane;
                 f[q][0] = a.src[lay.base(sid) + q * qp];
             } else if constexpr (LM == LM_BLOCKROWS) {
-                const char *p = reinterpret_cast<const char *>(a.src + rb[(ey(q) + 1) * 3 + ez(q) + 1]);
-                f[q][0] = *(reinterpret_cast<const T *>(p + LBM_U_SOFF(T, a, q)) - ex(q));
+                const char *p = s0 + nbc[(ey(q) + 1) * 3 + ez(q) + 1];
+                f[q][0] = *(reinterpret_cast<const T *>(p + LBM_U_GOFF(T, a, q, LM)) - ex(q));
             } else {
                 const char *p = ex(q) == 0 ? s0 : (ex(q) == 1 ? sm1 : sp1);
                 f[q][0] = ld_gather<T, ex(q)>(reinterpret_cast<const T *>(p + LBM_U_GOFF(T, a, q, LM)));
@@ -443,8 +459,8 @@ __device__ __forceinline__ void step_pull_cells(const StepArgs<T> &a, const int 
                 pe_m = p + (ex(q) == 1 ? lay.base(sid - 1) : 0);
                 pe_p = p + (ex(q) == -1 ? lay.base(sid + VEC) : 0);
             } else if constexpr (LM == LM_BLOCKROWS) {
-                const char *p = reinterpret_cast<const char *>(a.src + rb[(ey(q) + 1) * 3 + ez(q) + 1]);
-                const T *pv = reinterpret_cast<const T *>(p + LBM_U_SOFF(T, a, q));
+                const char *p = s0 + nbc[(ey(q) + 1) * 3 + ez(q) + 1];
+                const T *pv = reinterpret_cast<const T *>(p + LBM_U_GOFF(T, a, q, LM));
                 v = *reinterpret_cast<const V *>(pv);
                 pe_m = pv - 1;
                 pe_p = pv + VEC;
@@ -700,7 +716,7 @@ __global__ void __launch_bounds__(256) step_aa_kernel(const StepArgs<T> a)
     T *const lat = a.dst;
 
     long long b0, bm = 0, bp = 0;
-    long long rb[9];  // LM_BLOCKROWS, SHIFT: element index of (x, y - dy, z - dz, q = 0), see step_pull_cells
+    long long nbc[9];  // LM_BLOCKROWS, SHIFT: block-boundary correction towards row (y - dy, z - dz), see step_pull_cells
     if constexpr (LM == LM_ROWS) {
         const long long rowbase = rowid * Q;
         const int sm = (int)a.lay.smod;
@@ -716,16 +732,17 @@ __global__ void __launch_bounds__(256) step_aa_kernel(const StepArgs<T> a)
     } else if constexpr (LM == LM_BLOCKROWS) {
         b0 = a.lay.base(rowid) + x;
         if constexpr (SHIFT) {
+            const int r = (y + (z - a.zs0) * dim) & a.row_mask;
 #pragma unroll
             for (int dy = -1; dy <= 1; ++dy)
 #pragma unroll
                 for (int dz = -1; dz <= 1; ++dz)
-                    rb[(dy + 1) * 3 + dz + 1] = a.lay.base(rowid - (long long)dy * dim - (long long)dz * plane) + x;
+                    nbc[(dy + 1) * 3 + dz + 1] = (long long)((r - dy - dz * dim) >> a.row_shift) * a.blk18;
         }
     } else {
         b0 = a.lay.base(id0);
     }
-    (void)rb;
+    (void)nbc;
     char *const c0 = reinterpret_cast<char *>(lat + b0);
     char *const cm = reinterpret_cast<char *>(lat + bm);
     char *const cp = reinterpret_cast<char *>(lat + bp);
@@ -743,12 +760,8 @@ __global__ void __launch_bounds__(256) step_aa_kernel(const StepArgs<T> a)
             return lat + a.lay.base(nid) + (for_store ? q : opp(q)) * qp;
         } else if constexpr (LM == LM_BLOCKROWS) {
             // SHIFT: read (c - e_q, opp(q)), write (c + e_q, q)
-            if (for_store) {
-                char *p = reinterpret_cast<char *>(lat + rb[(-ey(q) + 1) * 3 - ez(q) + 1]);
-                return reinterpret_cast<T *>(p + a.soff[q]) + ex(q);
-            }
-            char *p = reinterpret_cast<char *>(lat + rb[(ey(q) + 1) * 3 + ez(q) + 1]);
-            return reinterpret_cast<T *>(p + a.soff[opp(q)]) - ex(q);
+            if (for_store) return reinterpret_cast<T *>(c0 + nbc[(-ey(q) + 1) * 3 - ez(q) + 1] + a.poff[q]) + ex(q);
+            return reinterpret_cast<T *>(c0 + nbc[(ey(q) + 1) * 3 + ez(q) + 1] + a.goff[q]) - ex(q);
         } else {
             // SHIFT: read (c - e_q, opp(q)), write (c + e_q, q): the same address for q and opp(q) swapped
             if (for_store) return reinterpret_cast<T *>((ex(q) == 0 ? c0 : (ex(q) == 1 ? cp : cm)) + a.poff[q]);

@@ -8,13 +8,13 @@ namespace {
 
 constexpr int TMA_SMEM_MAX = 200 * 1024;
 
-template <typename T, int TX>
-cudaError_t prepare_tx()
+template <typename T>
+cudaError_t prepare_t()
 {
     cudaError_t e = cudaSuccess;
-#define LBM_TMA_ATTR(F, M)                                                                                   \
-    if (e == cudaSuccess)                                                                                    \
-        e = cudaFuncSetAttribute(step_tma_kernel<T, F, M, TX>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+#define LBM_TMA_ATTR(F, M)                                                                               \
+    if (e == cudaSuccess)                                                                                \
+        e = cudaFuncSetAttribute(step_tma_kernel<T, F, M>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                  TMA_SMEM_MAX)
     LBM_TMA_ATTR(false, false);
     LBM_TMA_ATTR(false, true);
@@ -25,25 +25,16 @@ cudaError_t prepare_tx()
 }
 
 template <typename T>
-cudaError_t prepare_t()
-{
-    cudaError_t e = prepare_tx<T, 256>();
-    if (e == cudaSuccess) e = prepare_tx<T, 128>();
-    if (e == cudaSuccess) e = prepare_tx<T, 64>();
-    if (e == cudaSuccess) e = prepare_tx<T, 32>();
-    return e;
-}
-
-template <typename T, int TX>
 void go(const TmaCfg &k, const TmaArgs<T> &a, bool macro, int grid, cudaStream_t s)
 {
     const CUtensorMap &ms = *k.map_src, &md = *k.map_dst;
+    const int tx = k.tx;
     if (k.fast) {
-        if (macro) step_tma_kernel<T, true, true, TX><<<grid, TX, k.smem, s>>>(ms, md, a, k.error);
-        else step_tma_kernel<T, true, false, TX><<<grid, TX, k.smem, s>>>(ms, md, a, k.error);
+        if (macro) step_tma_kernel<T, true, true><<<grid, tx, k.smem, s>>>(ms, md, a, k.error);
+        else step_tma_kernel<T, true, false><<<grid, tx, k.smem, s>>>(ms, md, a, k.error);
     } else {
-        if (macro) step_tma_kernel<T, false, true, TX><<<grid, TX, k.smem, s>>>(ms, md, a, k.error);
-        else step_tma_kernel<T, false, false, TX><<<grid, TX, k.smem, s>>>(ms, md, a, k.error);
+        if (macro) step_tma_kernel<T, false, true><<<grid, tx, k.smem, s>>>(ms, md, a, k.error);
+        else step_tma_kernel<T, false, false><<<grid, tx, k.smem, s>>>(ms, md, a, k.error);
     }
 }
 
@@ -70,12 +61,7 @@ cudaError_t launch_tma(const TmaCfg &k, const StepArgs<T> &sa, int ns, bool macr
     for (int i = 0; i < 2; ++i)
         for (int q = 0; q < Q; ++q) a.stale[i][q] = sa.stale[i][q];
     const int grid = a.n_tiles < k.grid ? a.n_tiles : k.grid;
-    switch (k.tx) {
-        case 256: go<T, 256>(k, a, macro, grid, s); break;
-        case 128: go<T, 128>(k, a, macro, grid, s); break;
-        case 64: go<T, 64>(k, a, macro, grid, s); break;
-        default: go<T, 32>(k, a, macro, grid, s); break;
-    }
+    go<T>(k, a, macro, grid, s);
     return cudaGetLastError();
 }
 

@@ -89,13 +89,16 @@ __device__ __forceinline__ void tma_wait_read()
 __device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-template <typename T, bool FAST, bool MACRO, int TX>
-__global__ void __launch_bounds__(TX) step_tma_kernel(const __grid_constant__ CUtensorMap map_src,
-                                                       const __grid_constant__ CUtensorMap map_dst,
-                                                       const TmaArgs<T> a, int *__restrict__ error_flag)
+// TX = cells per row tile = threads per CTA (32, 64, 128 or 256) is the launch's blockDim.x, not a template
+// parameter: the kernel exists once per (T, FAST, MACRO) instead of four times.
+template <typename T, bool FAST, bool MACRO>
+__global__ void __launch_bounds__(256, sizeof(T) == 4 ? 4 : 2) step_tma_kernel(const __grid_constant__ CUtensorMap map_src,
+                                                        const __grid_constant__ CUtensorMap map_dst,
+                                                        const TmaArgs<T> a, int *__restrict__ error_flag)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr uint32_t STAGE_BYTES = Q * TX * sizeof(T);
+    const int TX = (int)blockDim.x;
+    const uint32_t STAGE_BYTES = (uint32_t)(Q * TX * sizeof(T));
     const int NS = a.ns;
     T *const ring = reinterpret_cast<T *>(smem_raw);                                   // [NS][Q][TX]
     uint64_t *const full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)NS * STAGE_BYTES);  // [NS]

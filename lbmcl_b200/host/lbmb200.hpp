@@ -35,7 +35,7 @@
 #include <vector>
 
 #include "../../include/lbm_b200.h"
-#include "fmt_e16.hpp"
+#include "vti_writer.hpp"
 
 #define LBM_INITIALIZE_KERNEL_NAME "initialize"
 #define LBM_COMPUTE_KERNEL_NAME "compute"
@@ -206,93 +206,10 @@ class LBMCL {
         std::fclose(fp);
     }
 
-    // ---- VTI output, lbmcl.hpp:261-334: rho then 3-component v over the wet cube, x fastest ----
-
-    // one z-plane of one array as text; every value is "%.16e " exactly as operator<< with std::scientific and
-    // precision 16 prints it
-    void formatPlane(std::string &out, int pass, size_t z, const T *rho, const T *u) const
-    {
-        const size_t from = 1, to = dim - 1, n = cells();
-        out.clear();
-        out.reserve((to - from) * (to - from) * (pass == 0 ? 25 : 75) + dim);
-        char tmp[3 * 32];
-        for (size_t y = from; y < to; ++y) {
-            for (size_t x = from; x < to; ++x) {
-                const size_t id = x + y * dim + z * dim * dim;
-                int len = 0;
-                if (pass == 0) {
-                    len = lbm_fmt::fmt_e16((double)rho[id], tmp);
-                    tmp[len++] = ' ';
-                } else {
-                    for (size_t c = 0; c < 3; ++c) {
-                        len += lbm_fmt::fmt_e16((double)u[c * n + id], tmp + len);
-                        tmp[len++] = ' ';
-                    }
-                }
-                out.append(tmp, (size_t)len);
-            }
-            out += '\n';
-        }
-    }
-
-    // Formats the planes of one array in batches of `nthreads` planes: while batch b is written, batch b+1 is
-    // being formatted, so that formatting and file I/O overlap and the text never exists in memory as a whole.
-    void writeArray(FILE *fp, int pass, const T *rho, const T *u, unsigned nthreads) const
-    {
-        const size_t planes = dim - 2;
-        const size_t per = nthreads;
-        const size_t n_batches = (planes + per - 1) / per;
-        std::vector<std::string> text[2];
-        text[0].resize(per);
-        text[1].resize(per);
-        auto format_batch = [&](size_t b, std::vector<std::string> &out) {
-            auto work = [&](size_t j) {
-                const size_t k = b * per + j;
-                if (k < planes) formatPlane(out[j], pass, 1 + k, rho, u);
-                else out[j].clear();
-            };
-            std::vector<std::thread> pool;
-            for (size_t j = 1; j < per; ++j) pool.emplace_back(work, j);
-            work(0);
-            for (auto &t : pool) t.join();
-        };
-        format_batch(0, text[0]);
-        for (size_t b = 0; b < n_batches; ++b) {
-            std::thread next;
-            if (b + 1 < n_batches) next = std::thread(format_batch, b + 1, std::ref(text[(b + 1) & 1]));
-            for (const std::string &c : text[b & 1]) std::fwrite(c.data(), 1, c.size(), fp);
-            if (next.joinable()) next.join();
-        }
-    }
-
+    // ---- VTI output, lbmcl.hpp:261-334 (vti_writer.hpp) ----
     void writeVTI(size_t iteration, const T *rho, const T *u) const
     {
-        FILE *fp = std::fopen(numbered(vtk_path, "lbmcl.", iteration, ".vti").c_str(), "w");
-        if (!fp) return;  // a missing directory is a silent no-op in the reference (no check on the ofstream)
-        std::vector<char> iobuf(8u << 20);
-        std::setvbuf(fp, iobuf.data(), _IOFBF, iobuf.size());
-        const size_t extent = dim - 3;
-        const char *type = std::is_same<T, float>::value ? "Float32" : "Float64";
-        std::fprintf(fp,
-                     "<?xml version=\"1.0\"?>\n"
-                     "<VTKFile type=\"ImageData\" version=\"0.1\" byte_order=\"LittleEndian\" header_type=\"UInt64\">\n"
-                     "  <ImageData WholeExtent=\"0 %zu 0 %zu 0 %zu\" Origin=\"0 0 0\" Spacing=\"1 1 1\">\n"
-                     "    <Piece Extent=\"0 %zu 0 %zu 0 %zu\">\n"
-                     "      <PointData Scalars=\"rho\">\n"
-                     "        <DataArray type=\"%s\" Name=\"rho\" NumberOfComponents=\"1\" format=\"ascii\">\n",
-                     extent, extent, extent, extent, extent, extent, type);
-        unsigned nthreads = std::thread::hardware_concurrency();
-        if (nthreads == 0) nthreads = 1;
-        if (nthreads > 32) nthreads = 32;
-        if (nthreads > dim - 2) nthreads = (unsigned)(dim - 2);
-        writeArray(fp, 0, rho, u, nthreads);
-        std::fprintf(fp,
-                     "        </DataArray>\n"
-                     "        <DataArray type=\"%s\" Name=\"v\" NumberOfComponents=\"3\" format=\"ascii\">\n",
-                     type);
-        writeArray(fp, 1, rho, u, nthreads);
-        std::fputs("        </DataArray>\n      </PointData>\n    </Piece>\n  </ImageData>\n</VTKFile>\n", fp);
-        std::fclose(fp);
+        lbm_vti::write_vti<T>(numbered(vtk_path, "lbmcl.", iteration, ".vti"), dim, rho, u, 0);
     }
 
     // The reference's storeData(it) (blocking reads + file, lbmcl.hpp:261-334) as a pipeline stage.  Called

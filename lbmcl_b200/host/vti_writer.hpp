@@ -1,0 +1,159 @@
+// The VTI writer of the LBMCL host program: lbmcl.<it>.vti as the reference writes it (lbmcl.hpp:261-334) --
+// ASCII ImageData, WholeExtent 0..DIM-3 per axis, `rho` then the 3-component `v` over the wet cube
+// x,y,z in [1, DIM-2], x fastest, every value printed as std::scientific << std::setprecision(16) followed by a
+// blank, one text line per x-row -- byte for byte, but written by several threads:
+//   each worker formats one z-plane per round (exact "%.16e", fmt_e16.hpp), learns its file offset from the
+//   sizes of the planes before it, and writes its text itself (pwrite), so that formatting AND the copy into
+//   the page cache run in parallel and the text never exists in memory as a whole.
+// ASCII output dominates every `-e N` run (1.5 GB per file at 256^3).
+#pragma once
+
+#include <fcntl.h>
+#include <unistd.h>
+
+#include <condition_variable>
+#include <cstdio>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <type_traits>
+#include <vector>
+
+#include "fmt_e16.hpp"
+
+namespace lbm_vti {
+
+struct Barrier {  // C++11 has none
+    std::mutex m;
+    std::condition_variable cv;
+    unsigned n, count = 0, generation = 0;
+    explicit Barrier(unsigned n) : n(n) {}
+    void wait()
+    {
+        std::unique_lock<std::mutex> l(m);
+        const unsigned g = generation;
+        if (++count == n) {
+            count = 0;
+            ++generation;
+            cv.notify_all();
+        } else {
+            cv.wait(l, [&] { return g != generation; });
+        }
+    }
+};
+
+inline void write_at(int fd, const char *p, size_t n, size_t off)
+{
+    while (n > 0) {
+        const ssize_t w = ::pwrite(fd, p, n, (off_t)off);
+        if (w <= 0) return;  // disk full etc.: like the reference's unchecked ofstream, the file is just short
+        p += w;
+        n -= (size_t)w;
+        off += (size_t)w;
+    }
+}
+
+// one z-plane of one array as text (pass 0: rho, pass 1: v)
+template <typename T>
+void format_plane(std::string &out, size_t dim, int pass, size_t z, const T *rho, const T *u)
+{
+    const size_t from = 1, to = dim - 1, n = dim * dim * dim;
+    out.clear();
+    out.reserve((to - from) * (to - from) * (pass == 0 ? 25 : 75) + dim);
+    char tmp[3 * 32];
+    for (size_t y = from; y < to; ++y) {
+        for (size_t x = from; x < to; ++x) {
+            const size_t id = x + y * dim + z * dim * dim;
+            int len = 0;
+            if (pass == 0) {
+                len = lbm_fmt::fmt_e16((double)rho[id], tmp);
+                tmp[len++] = ' ';
+            } else {
+                for (size_t c = 0; c < 3; ++c) {
+                    len += lbm_fmt::fmt_e16((double)u[c * n + id], tmp + len);
+                    tmp[len++] = ' ';
+                }
+            }
+            out.append(tmp, (size_t)len);
+        }
+        out += '\n';
+    }
+}
+
+// One array of the file, starting at byte `base`; returns the new end of the file.
+template <typename T>
+size_t write_array(int fd, size_t base, size_t dim, int pass, const T *rho, const T *u, unsigned nthreads)
+{
+    const size_t planes = dim - 2;
+    const size_t rounds = (planes + nthreads - 1) / nthreads;
+    std::vector<std::string> text(nthreads);
+    std::vector<size_t> size(nthreads, 0);
+    Barrier bar(nthreads);
+    size_t end = base;  // every worker advances its own copy of the base identically; worker 0 reports it
+    auto work = [&](unsigned j) {
+        size_t my_base = base;
+        for (size_t r = 0; r < rounds; ++r) {
+            const size_t k = r * nthreads + j;
+            if (k < planes) format_plane<T>(text[j], dim, pass, 1 + k, rho, u);
+            else text[j].clear();
+            size[j] = text[j].size();
+            bar.wait();  // every size of this round is known
+            size_t before = 0, total = 0;
+            for (unsigned i = 0; i < nthreads; ++i) {
+                if (i < j) before += size[i];
+                total += size[i];
+            }
+            write_at(fd, text[j].data(), text[j].size(), my_base + before);
+            my_base += total;
+            bar.wait();  // everybody has read the sizes: they may be overwritten
+        }
+        if (j == 0) end = my_base;
+    };
+    std::vector<std::thread> pool;
+    for (unsigned j = 1; j < nthreads; ++j) pool.emplace_back(work, j);
+    work(0);
+    for (auto &t : pool) t.join();
+    return end;
+}
+
+// rho[N], u[3][N] in the reference's global layouts (kernels.cl:67-70).  nthreads == 0: one per core, at most
+// 32.  A path that cannot be opened is a silent no-op, as in the reference (no check on its ofstream).
+template <typename T>
+void write_vti(const std::string &path, size_t dim, const T *rho, const T *u, unsigned nthreads)
+{
+    const int fd = ::open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0) return;
+    const size_t extent = dim - 3;
+    const char *type = std::is_same<T, float>::value ? "Float32" : "Float64";
+    char head[1024];
+    int n = std::snprintf(head, sizeof head,
+                          "<?xml version=\"1.0\"?>\n"
+                          "<VTKFile type=\"ImageData\" version=\"0.1\" byte_order=\"LittleEndian\" header_type=\"UInt64\">\n"
+                          "  <ImageData WholeExtent=\"0 %zu 0 %zu 0 %zu\" Origin=\"0 0 0\" Spacing=\"1 1 1\">\n"
+                          "    <Piece Extent=\"0 %zu 0 %zu 0 %zu\">\n"
+                          "      <PointData Scalars=\"rho\">\n"
+                          "        <DataArray type=\"%s\" Name=\"rho\" NumberOfComponents=\"1\" format=\"ascii\">\n",
+                          extent, extent, extent, extent, extent, extent, type);
+    size_t pos = 0;
+    write_at(fd, head, (size_t)n, pos);
+    pos += (size_t)n;
+    if (nthreads == 0) {
+        nthreads = std::thread::hardware_concurrency();
+        if (nthreads == 0) nthreads = 1;
+        if (nthreads > 32) nthreads = 32;
+    }
+    if (nthreads > dim - 2) nthreads = (unsigned)(dim - 2);
+    pos = write_array<T>(fd, pos, dim, 0, rho, u, nthreads);
+    n = std::snprintf(head, sizeof head,
+                      "        </DataArray>\n"
+                      "        <DataArray type=\"%s\" Name=\"v\" NumberOfComponents=\"3\" format=\"ascii\">\n",
+                      type);
+    write_at(fd, head, (size_t)n, pos);
+    pos += (size_t)n;
+    pos = write_array<T>(fd, pos, dim, 1, rho, u, nthreads);
+    const char tail[] = "        </DataArray>\n      </PointData>\n    </Piece>\n  </ImageData>\n</VTKFile>\n";
+    write_at(fd, tail, sizeof tail - 1, pos);
+    ::close(fd);
+}
+
+}  // namespace lbm_vti
