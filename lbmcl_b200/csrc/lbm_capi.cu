@@ -594,22 +594,20 @@ static int setup_tma(lbm_ctx *c, int n_sm)
     // so the shallowest ring with the most resident CTAs wins: 2 stages, as many CTAs as fit in 200 KB
     const size_t stage = (size_t)Q * c->tma_tx * c->esize;
     int ns = 2;
-    int ctas = (int)((200 * 1024) / (2 * stage + 1024));
-    const int by_registers = c->p.precision == LBM_F32 ? 4 : 2;  // the kernels' __launch_bounds__ (lbm_tma.cuh)
-    if (ctas > by_registers) ctas = by_registers;
     if (const char *e = std::getenv("LBM_TMA_NS")) ns = std::atoi(e);
-    if (const char *e = std::getenv("LBM_TMA_CTAS")) ctas = std::atoi(e);
     if (ns < 2) ns = 2;
-    if (ctas < 1) ctas = 1;
     while (ns > 2 && (size_t)ns * stage + 64 > 200 * 1024) --ns;
     c->tma_ns = ns;
     c->tma_smem = (size_t)ns * stage + (size_t)ns * sizeof(uint64_t);
     if (c->tma_smem > 200 * 1024) return fail(c, LBM_ERR_INVALID, "TMA variant: tile ring does not fit shared memory");
-    c->tma_grid = ctas * n_sm;
     LBM_CUDA(c, cudaMalloc(&c->tma_error, sizeof(int)));
     LBM_CUDA(c, cudaMemset(c->tma_error, 0, sizeof(int)));
     // opt in to the large dynamic shared memory once per device (never inside a stream capture)
     LBM_CUDA(c, tma_prepare(c->device));
+    // one wave of persistent CTAs: as many per SM as registers and shared memory allow
+    int ctas = tma_resident_ctas(c->p.precision == LBM_F64, c->tma_tx, c->tma_smem, c->p.fast_math != 0);
+    if (const char *e = std::getenv("LBM_TMA_CTAS")) ctas = std::atoi(e) > 0 ? std::atoi(e) : ctas;
+    c->tma_grid = ctas * n_sm;
     return LBM_OK;
 }
 

@@ -53,6 +53,7 @@ struct TmaCfg {
     bool fast;
 };
 cudaError_t tma_prepare(int device);  // once per device: opt in to > 48 KB dynamic shared memory
+int tma_resident_ctas(bool f64, int tx, size_t smem, bool fast);  // CTAs per SM by registers and shared memory
 cudaError_t launch_tma_f32(const TmaCfg &, const StepArgs<float> &, int ns, bool macro, cudaStream_t);
 cudaError_t launch_tma_f64(const TmaCfg &, const StepArgs<double> &, int ns, bool macro, cudaStream_t);
 

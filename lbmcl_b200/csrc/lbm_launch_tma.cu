@@ -65,7 +65,34 @@ cudaError_t launch_tma(const TmaCfg &k, const StepArgs<T> &sa, int ns, bool macr
     return cudaGetLastError();
 }
 
+template <typename T>
+int resident_ctas(int tx, size_t smem, bool fast)
+{
+    int n = 0, m = 0;
+    cudaError_t e;
+    if (fast) {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, step_tma_kernel<T, true, false>, tx, smem);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m, step_tma_kernel<T, true, true>, tx, smem);
+    } else {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, step_tma_kernel<T, false, false>, tx, smem);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m, step_tma_kernel<T, false, true>, tx, smem);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return 1;
+    }
+    n = n < m ? n : m;
+    return n < 1 ? 1 : n;
+}
+
 }  // namespace
+
+// How many CTAs of the TMA kernels fit one SM (registers and shared memory): the persistent grid is exactly that
+// many per SM, so that it runs as ONE wave.
+int tma_resident_ctas(bool f64, int tx, size_t smem, bool fast)
+{
+    return f64 ? resident_ctas<double>(tx, smem, fast) : resident_ctas<float>(tx, smem, fast);
+}
 
 // The opt-in to more than 48 KB of dynamic shared memory is per function and per device; done once per
 // device when the first TMA context is created there (not per launch: launches may be inside a stream capture).

@@ -92,7 +92,7 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // TX = cells per row tile = threads per CTA (32, 64, 128 or 256) is the launch's blockDim.x, not a template
 // parameter: the kernel exists once per (T, FAST, MACRO) instead of four times.
 template <typename T, bool FAST, bool MACRO>
-__global__ void __launch_bounds__(256, sizeof(T) == 4 ? 4 : 2) step_tma_kernel(const __grid_constant__ CUtensorMap map_src,
+__global__ void __launch_bounds__(256) step_tma_kernel(const __grid_constant__ CUtensorMap map_src,
                                                         const __grid_constant__ CUtensorMap map_dst,
                                                         const TmaArgs<T> a, int *__restrict__ error_flag)
 {
