@@ -362,7 +362,8 @@ def parity_gate(rank, world, local_rank, dev, transport):
         dist.barrier()          # nobody frees a lattice a neighbour may still be storing into
         sim.close()
         if rank == 0:
-            from oracle import Oracle
+            from oracle import Oracle, host_cores
+            Oracle(precision).set_threads(host_cores())   # torchrun exports OMP_NUM_THREADS=1
             n_slab = (dim // world) * dim * dim
             parts = [o.cpu().numpy().view(npd) for o in out]
             g_rho = np.concatenate([p[:n_slab] for p in parts])
