@@ -171,6 +171,7 @@ LaunchCfg launch_cfg(const lbm_ctx *c, int peer_mode)
     k.dim = c->dim;
     k.lm = peer_mode != PEER_NONE ? c->layout_natural : c->layout_mode;
     k.fast = c->p.fast_math != 0;
+    k.aa_unaligned = c->aa_unaligned;
     return k;
 }
 
@@ -982,6 +983,8 @@ int lbm_create(const lbm_params *p, lbm_ctx **out)
     const int vmax = p->precision == LBM_F32 ? 4 : 2;
     int vec = (p->variant == LBM_VARIANT_VEC2 || p->variant == LBM_VARIANT_VEC4) ? p->variant : 1;
     c->aa = p->variant == LBM_VARIANT_AA;
+    c->aa_unaligned = p->reserved[2] == 1;  // test / A-B hook: the per-thread x +- 1 form of the SHIFT step
+    if (const char *v = std::getenv("LBM_AA_SHIFT")) c->aa_unaligned = c->aa_unaligned || std::strcmp(v, "unaligned") == 0;
     if (p->variant == LBM_VARIANT_TMA) {
         // eligibility; otherwise the scalar kernel is used
         c->tma = p->stride <= p->dim && p->stride * (long long)(p->precision == LBM_F32 ? 4 : 8) >= 16 && p->dim >= 32;

@@ -49,6 +49,7 @@ struct lbm_ctx {
     int layout_mode = lbm::LM_GENERIC;     // what non-peer launches use (test hook: may be LM_GENERIC)
     int layout_natural = lbm::LM_GENERIC;  // what stride and DIM call for
     bool aa = false;             // in-place AA variant: only f[0] exists
+    bool aa_unaligned = false;   // AA: SHIFT step with per-thread x +- 1 accesses instead of the aligned kernel
     bool tma = false;            // TMA-fed variant: tensor maps of the two lattices
     CUtensorMap tmap[2];
     int tma_tx = 0, tma_ns = 0, tma_grid = 0;

@@ -17,6 +17,7 @@ struct LaunchCfg {
     int dim;
     int lm;           // LM_* addressing mode
     bool fast;        // -o
+    bool aa_unaligned = false;  // AA variant: the SHIFT step with per-thread x +- 1 accesses (cross-check / A-B)
 };
 
 // grid of a pull / AA launch over `n_planes` planes

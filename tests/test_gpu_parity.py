@@ -122,6 +122,38 @@ def test_generic_addressing_equals_fast_addressing(variant, precision):
         assert rho.tobytes() == exp["rho"].tobytes() and u.tobytes() == exp["u"].tobytes()
 
 
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+@pytest.mark.parametrize("dim,stride,block", [
+    (64, 32, None),            # two warps per row: the x shift crosses a warp edge through shared memory
+    (64, 32, (32, 8, 1)),      # one warp per block, two blocks per row: block edges use the direct accesses
+    (128, 32, (64, 4, 1)),     # warp edges AND block edges inside a row
+    (64, 64, None),            # stride == DIM
+    (64, 512, None),           # LM_BLOCKROWS (a CSoA block holds 8 rows)
+    (64, 262144, None),        # LM_SOA
+    (32, 8, None),             # stride < warp: a warp's 32 cells span four CSoA runs
+])
+def test_aa_shift_step_aligned_and_unaligned_kernels_match_the_oracle(dim, stride, block, precision):
+    """The in-place variant's SHIFT step exists in two forms: every thread accessing x +- 1 itself
+    (step_aa_kernel<SHIFT>, the round-1 kernel, now the cross-check) and the aligned form that moves values
+    between lanes by shuffle / shared memory (step_aa_shift_aligned_kernel, default).  Both must reproduce the
+    oracle bit for bit: rho/u snapshots and the complete -f view (which also shows the pushes into WALL cells),
+    after an even and an odd number of iterations."""
+    every = 2
+    kw = dict(dim=dim, precision=precision, stride=stride, variant=8)
+    if block is not None:
+        kw.update(block=block, exact_block=True)
+    for its in (4, 5):
+        exp = Oracle(precision).run(dim, stride, 0.0089, 0.05, its, every, keep_state=True)
+        st = exp["state"]
+        want_f = (st["f_stream"] if (its + 1) % 2 == 0 else st["f_collide"]).tobytes()
+        for unaligned in (False, True):
+            with _sim(aa_unaligned_shift=unaligned, **kw) as s:
+                rho, u = s.run_snapshots(its, every)
+                got_f = s.read_f()
+            assert rho.tobytes() == exp["rho"].tobytes() and u.tobytes() == exp["u"].tobytes(), (its, unaligned)
+            assert got_f.tobytes() == want_f, (its, unaligned)
+
+
 def test_step_api_equals_run_api():
     """lbm_step (one reference `compute` launch) and lbm_run (the loop) are the same path."""
     dim, stride, its, every = 16, 16, 9, 3
