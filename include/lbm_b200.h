@@ -85,8 +85,7 @@ typedef struct lbm_params {
     int32_t z_begin;       /* owned global planes [z_begin, z_end); 0, DIM for a single device      */
     int32_t z_end;
     int32_t reserved[8];   /* zero, except the tuning/test hooks: [0] = 1 forces the generic CSoA
-                              addressing, [1] = 1 honours block_x/y/z exactly, [2] = 1 runs the
-                              in-place variant's SHIFT step with per-thread x+-1 accesses           */
+                              addressing, [1] = 1 honours block_x/y/z exactly                        */
 } lbm_params;
 
 typedef struct lbm_ctx lbm_ctx;

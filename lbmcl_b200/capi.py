@@ -146,7 +146,7 @@ def load() -> ctypes.CDLL:
 
 def make_params(dim=8, precision="f32", viscosity=0.0089, velocity=0.05, stride=32, block=(8, 8, 8),
                 fast_math=False, device=-1, variant=VARIANT_AUTO, z_range=None, exact_block=False,
-                generic_addressing=False, aa_unaligned_shift=False) -> LbmParams:
+                generic_addressing=False) -> LbmParams:
     lib = load()
     p = LbmParams()
     lib.lbm_default_params(ctypes.byref(p))
@@ -168,7 +168,6 @@ def make_params(dim=8, precision="f32", viscosity=0.0089, velocity=0.05, stride=
         p.z_begin, p.z_end = z_range
     p.reserved[0] = 1 if generic_addressing else 0
     p.reserved[1] = 1 if exact_block else 0
-    p.reserved[2] = 1 if aa_unaligned_shift else 0
     return p
 
 

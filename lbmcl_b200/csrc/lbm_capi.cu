@@ -171,7 +171,6 @@ LaunchCfg launch_cfg(const lbm_ctx *c, int peer_mode)
     k.dim = c->dim;
     k.lm = peer_mode != PEER_NONE ? c->layout_natural : c->layout_mode;
     k.fast = c->p.fast_math != 0;
-    k.aa_unaligned = c->aa_unaligned;
     return k;
 }
 
@@ -228,7 +227,8 @@ cudaError_t launch_step_p(lbm_ctx *c, const Planes &pl, bool macro, int peer_mod
     if (c->tma && plain) {
         TmaCfg t{};
         t.map_src = &c->tmap[c->cur];
-        t.map_dst = &c->tmap[c->cur ^ 1];
+        t.map_dst = &c->tmap_st[c->cur ^ 1];
+        t.osdiv = c->tma_osdiv;
         t.tx = c->tma_tx;
         t.grid = c->tma_grid;
         t.smem = c->tma_smem;
@@ -574,32 +574,43 @@ static int setup_tma(lbm_ctx *c, int n_sm)
     EncodeFn encode = reinterpret_cast<EncodeFn>(fn);
 
     const long long S = c->lay.qpitch();
+    // cells per row tile = consumer threads per CTA (measured: 256 beats 128 and 64 in both precisions)
     c->tma_tx = c->dim < 256 ? c->dim : 256;
-    if (const char *e = std::getenv("LBM_TMA_TX")) {  // test hook: narrower tiles => several segments per row
+    if (const char *e = std::getenv("LBM_TMA_TX")) {  // test / tuning hook: other tile widths (several segments per row)
         const int v = std::atoi(e);
         if ((v == 32 || v == 64 || v == 128 || v == 256) && v <= c->dim) c->tma_tx = v;
     }
     const cuuint64_t gdim[3] = {(cuuint64_t)S, (cuuint64_t)Q, (cuuint64_t)(c->n_alloc / S)};
     const cuuint64_t gstride[2] = {(cuuint64_t)(S * c->esize), (cuuint64_t)(Q * S * c->esize)};
     const cuuint32_t b0 = (cuuint32_t)(S < c->tma_tx ? S : c->tma_tx);
-    const cuuint32_t box[3] = {b0, 1u, (cuuint32_t)(c->tma_tx / b0)};
+    const cuuint32_t box[3] = {b0, 1u, (cuuint32_t)(c->tma_tx / b0)};        // loads: one direction of one row tile
+    const cuuint32_t s32 = (cuuint32_t)(S < 32 ? S : 32);
+    const cuuint32_t box_st[3] = {s32, (cuuint32_t)Q, 32u / s32};             // stores: one warp's cells, all directions
+    c->tma_osdiv = ilog2(s32);
     const cuuint32_t estr[3] = {1u, 1u, 1u};
     const CUtensorMapDataType dt = c->p.precision == LBM_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64;
     for (int i = 0; i < 2; ++i) {
-        const CUresult r = encode(&c->tmap[i], dt, 3, c->f[i], gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        CUresult r = encode(&c->tmap[i], dt, 3, c->f[i], gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r == CUDA_SUCCESS)
+            r = encode(&c->tmap_st[i], dt, 3, c->f[i], gdim, gstride, box_st, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(c, LBM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     }
-    // ring depth / resident CTAs (profiles/r01_tma_experiment.md): the kernel is latency-bound per CTA,
-    // so the shallowest ring with the most resident CTAs wins: 2 stages, as many CTAs as fit in 200 KB
+    // shared memory of one CTA: NS input tiles [Q][TX], (bulk-store build only) two output tiles [Q][32] per
+    // consumer warp, 2 NS mbarriers + NS tile coordinates.  The producer warp keeps NS - 1 tiles in flight ahead of
+    // the consumers.  Measured (profiles/r02_tma_experiment.md): 2, 3 or 4 stages and 2, 3 or 4 CTAs per SM all land
+    // within 5 % of each other (the kernel is bound by instruction issue, not by latency), 2 stages marginally best.
     const size_t stage = (size_t)Q * c->tma_tx * c->esize;
+    const size_t outs = tma_direct_store() ? 0 : (size_t)(c->tma_tx / 32) * 2 * Q * 32 * c->esize;
+    const size_t fixed = outs + 256;
     int ns = 2;
     if (const char *e = std::getenv("LBM_TMA_NS")) ns = std::atoi(e);
     if (ns < 2) ns = 2;
-    while (ns > 2 && (size_t)ns * stage + 64 > 200 * 1024) --ns;
+    while (ns > 2 && (size_t)ns * stage + fixed > 200 * 1024) --ns;
     c->tma_ns = ns;
-    c->tma_smem = (size_t)ns * stage + (size_t)ns * sizeof(uint64_t);
+    c->tma_smem = (size_t)ns * stage + outs + (size_t)ns * (2 * sizeof(uint64_t) + 16) + 16;
     if (c->tma_smem > 200 * 1024) return fail(c, LBM_ERR_INVALID, "TMA variant: tile ring does not fit shared memory");
     LBM_CUDA(c, cudaMalloc(&c->tma_error, sizeof(int)));
     LBM_CUDA(c, cudaMemset(c->tma_error, 0, sizeof(int)));
@@ -983,8 +994,6 @@ int lbm_create(const lbm_params *p, lbm_ctx **out)
     const int vmax = p->precision == LBM_F32 ? 4 : 2;
     int vec = (p->variant == LBM_VARIANT_VEC2 || p->variant == LBM_VARIANT_VEC4) ? p->variant : 1;
     c->aa = p->variant == LBM_VARIANT_AA;
-    c->aa_unaligned = p->reserved[2] == 1;  // test / A-B hook: the per-thread x +- 1 form of the SHIFT step
-    if (const char *v = std::getenv("LBM_AA_SHIFT")) c->aa_unaligned = c->aa_unaligned || std::strcmp(v, "unaligned") == 0;
     if (p->variant == LBM_VARIANT_TMA) {
         // eligibility; otherwise the scalar kernel is used
         c->tma = p->stride <= p->dim && p->stride * (long long)(p->precision == LBM_F32 ? 4 : 8) >= 16 && p->dim >= 32;

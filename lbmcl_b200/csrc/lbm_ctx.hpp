@@ -49,9 +49,10 @@ struct lbm_ctx {
     int layout_mode = lbm::LM_GENERIC;     // what non-peer launches use (test hook: may be LM_GENERIC)
     int layout_natural = lbm::LM_GENERIC;  // what stride and DIM call for
     bool aa = false;             // in-place AA variant: only f[0] exists
-    bool aa_unaligned = false;   // AA: SHIFT step with per-thread x +- 1 accesses instead of the aligned kernel
     bool tma = false;            // TMA-fed variant: tensor maps of the two lattices
-    CUtensorMap tmap[2];
+    CUtensorMap tmap[2];         // loads: box = one direction of one row tile
+    CUtensorMap tmap_st[2];      // stores: box = one warp's 32 cells x 19 directions
+    int tma_osdiv = 5;           // log2(min(stride, 32))
     int tma_tx = 0, tma_ns = 0, tma_grid = 0;
     size_t tma_smem = 0;
     int *tma_error = nullptr;    // device flag set by a kernel whose mbarrier wait timed out

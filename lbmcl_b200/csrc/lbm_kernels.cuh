@@ -323,12 +323,6 @@ __device__ __forceinline__ T ld_gather(const T *p)
 #endif
 }
 
-// the five directions with ex = +1 / ex = -1
-__host__ __device__ constexpr int aa_xp(int k) { return k == 0 ? 1 : k == 1 ? 7 : k == 2 ? 10 : k == 3 ? 11 : 15; }
-__host__ __device__ constexpr int aa_xm(int k) { return k == 0 ? 3 : k == 1 ? 8 : k == 2 ? 9 : k == 3 ? 13 : 17; }
-static_assert(ex(aa_xp(0)) == 1 && ex(aa_xp(1)) == 1 && ex(aa_xp(2)) == 1 && ex(aa_xp(3)) == 1 && ex(aa_xp(4)) == 1, "ex = +1");
-static_assert(ex(aa_xm(0)) == -1 && ex(aa_xm(1)) == -1 && ex(aa_xm(2)) == -1 && ex(aa_xm(3)) == -1 && ex(aa_xm(4)) == -1, "ex = -1");
-
 // ---- in-kernel slab ordering (PEER_FLAGS) ----
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p)
 {
@@ -435,59 +429,6 @@ __device__ __forceinline__ void step_pull_cells(const StepArgs<T> &a, const int 
 
     // ---- gather: f[q][j] = G(x0 + j - ex, y - ey, z - ez, q) ----
     T f[Q][VEC];
-#ifdef LBM_PULL_ALIGNED
-    // A/B build (profiles/r02_experiments.md §5): every lane loads at its OWN x (one full 128-byte line per warp and
-    // direction), the x +- 1 shift is a warp shuffle, the value at a warp edge comes from the neighbouring warp of the
-    // block through shared memory; only the two threads at a block edge inside a row load x -+ 1 themselves.
-    // Needs blockDim.x % 32 == 0 and every warp of the block at the barrier (step_pull_body).
-    if constexpr (VEC == 1 && LM != LM_GENERIC) {
-        __shared__ T edge[2][5][8];
-        const int lane = tx & 31;
-        const int warp = (tx + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z)) >> 5;
-        static_for<Q>([&](auto qc) {
-            constexpr int q = decltype(qc)::value;
-            if constexpr (LM == LM_BLOCKROWS) {
-                f[q][0] = *reinterpret_cast<const T *>(s0 + nbc[(ey(q) + 1) * 3 + ez(q) + 1] + LBM_U_GOFF(T, a, q, LM));
-            } else {
-                f[q][0] = *reinterpret_cast<const T *>(s0 + LBM_U_GOFF(T, a, q, LM));
-            }
-        });
-        if (lane == 31) {
-#pragma unroll
-            for (int k = 0; k < 5; ++k) edge[0][k][warp] = f[aa_xp(k)][0];
-        }
-        if (lane == 0) {
-#pragma unroll
-            for (int k = 0; k < 5; ++k) edge[1][k][warp] = f[aa_xm(k)][0];
-        }
-        __syncthreads();
-        const bool first_in_block = tx == 0, last_in_block = tx == (int)blockDim.x - 1;
-        static_for<5>([&](auto kc) {
-            constexpr int k = decltype(kc)::value;
-            constexpr int qp = aa_xp(k), qm = aa_xm(k);
-            T vp = __shfl_up_sync(mask, f[qp][0], 1);
-            T vm = __shfl_down_sync(mask, f[qm][0], 1);
-            if (lane == 0) {
-                if (!first_in_block) vp = edge[0][k][warp - 1];
-                else if (x0 > 0) {
-                    if constexpr (LM == LM_BLOCKROWS)
-                        vp = *(reinterpret_cast<const T *>(s0 + nbc[(ey(qp) + 1) * 3 + ez(qp) + 1] + LBM_U_GOFF(T, a, qp, LM)) - 1);
-                    else vp = *reinterpret_cast<const T *>(sm1 + LBM_U_GOFF(T, a, qp, LM));
-                }
-            }
-            if (lane == 31) {
-                if (!last_in_block) vm = edge[1][k][warp + 1];
-                else if (x0 + 1 < dim) {
-                    if constexpr (LM == LM_BLOCKROWS)
-                        vm = *(reinterpret_cast<const T *>(s0 + nbc[(ey(qm) + 1) * 3 + ez(qm) + 1] + LBM_U_GOFF(T, a, qm, LM)) + 1);
-                    else vm = *reinterpret_cast<const T *>(sp1 + LBM_U_GOFF(T, a, qm, LM));
-                }
-            }
-            f[qp][0] = vp;
-            f[qm][0] = vm;
-        });
-    } else
-#endif
     if constexpr (VEC == 1) {
         static_for<Q>([&](auto qc) {
             constexpr int q = decltype(qc)::value;
@@ -710,14 +651,6 @@ __device__ __forceinline__ void step_pull_body(const StepArgs<T> &a)
             if (live) step_pull_cells<T, VEC, FAST, MACRO, PEER_NONE, LM>(a, x0, y, z, rowbits, mask);
         }
     } else {
-#ifdef LBM_PULL_ALIGNED
-        if constexpr (VEC == 1 && LM != LM_GENERIC) {
-            if (!live) {
-                __syncthreads();  // the one barrier of step_pull_cells (a warp lies inside one row: warp-uniform)
-                return;
-            }
-        }
-#endif
         if (!live) return;
         step_pull_cells<T, VEC, FAST, MACRO, PEER, LM>(a, x0, y, z, rowbits, mask);
     }
@@ -766,20 +699,19 @@ __global__ void __launch_bounds__(256, step_min_blocks<T, VEC, MACRO, PEER>()) s
 // here they are replaced explicitly by their initial value (the `stale` constants) using the cell's
 // side bits, for all six walls.
 //
-// Occupancy: step_aa_kernel is left to ptxas (40 registers in fp32 LOCAL, 73-80 in fp64 without a bound; a
-// bound of 6 blocks makes ptxas spill 196 bytes at the very same 40 registers).  The aligned SHIFT kernel is
-// pinned like the pull kernel (step_min_blocks): 6 blocks of 256 threads per SM in fp32 (40 registers, 16 bytes
-// spilled; unbounded it takes 56 = 4 blocks), 3 in fp64 (80 registers, no spills).
+// Occupancy: left to ptxas by default (fp32: 40 registers LOCAL / 48 SHIFT, fp64: 73 / 80, no spills).  A bound of
+// 6 blocks per SM makes ptxas spill 196 bytes in the LOCAL step at the very same 40 registers, so only the SHIFT
+// step takes an optional bound (-DLBM_MINB_AA_SHIFT_F32=6: 40 registers, 16-28 bytes spilled; an A/B knob).
 #ifndef LBM_MINB_AA_SHIFT_F32
-#define LBM_MINB_AA_SHIFT_F32 6
+#define LBM_MINB_AA_SHIFT_F32 0
 #endif
 #ifndef LBM_MINB_AA_SHIFT_F64
-#define LBM_MINB_AA_SHIFT_F64 3
+#define LBM_MINB_AA_SHIFT_F64 0
 #endif
-template <typename T>
-__host__ __device__ constexpr int aa_shift_min_blocks()
+template <typename T, bool SHIFT>
+__host__ __device__ constexpr int aa_min_blocks()
 {
-    return sizeof(T) == 4 ? LBM_MINB_AA_SHIFT_F32 : LBM_MINB_AA_SHIFT_F64;
+    return !SHIFT ? 0 : (sizeof(T) == 4 ? LBM_MINB_AA_SHIFT_F32 : LBM_MINB_AA_SHIFT_F64);
 }
 
 // In-place kernels, after the gather: ghost constants for populations that would arrive from a WALL cell,
@@ -820,7 +752,7 @@ __device__ __forceinline__ int aa_collide_cell(const StepArgs<T> &a, T (&f)[Q], 
 }
 
 template <typename T, bool FAST, bool MACRO, bool SHIFT, int LM>
-__global__ void __launch_bounds__(256) step_aa_kernel(const StepArgs<T> a)
+__global__ void __launch_bounds__(256, aa_min_blocks<T, SHIFT>()) step_aa_kernel(const StepArgs<T> a)
 {
     const int dim = a.dim;
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -905,177 +837,6 @@ __global__ void __launch_bounds__(256) step_aa_kernel(const StepArgs<T> a)
             a.u[id0] = ux;
             a.u[a.n_local + id0] = uy;
             a.u[2 * a.n_local + id0] = uz;
-        }
-    }
-}
-
-// SHIFT step with ALIGNED accesses (the default where a block holds whole warps of one row, bx % 32 == 0).
-//
-// step_aa_kernel<SHIFT> lets thread x read A(x - ex, ..) and write A(x + ex, ..): for the ten directions with
-// ex != 0 a warp's 32 elements then straddle two 128-byte lines -- with the default CSoA stride of 32 the odd
-// element even lies 19 runs away -- and the STORES become partial-sector writes that the L2 has to merge
-// (ncu, round 1: 4.46 sectors per request on loads and stores; 1024^3: 27.4 ms against 23.2 ms for the LOCAL step).
-// Here thread x touches only addresses with ITS OWN x:
-//   load   a_q(x) = A(x, y - ey, z - ez, opp(q))                 one full line per warp and direction
-//   gather f_q(x) = a_q(x - ex)                                  warp shuffle; the lane at a warp edge takes the value of
-//                                                                the neighbouring warp from shared memory
-//   collide
-//   scatter g_q(x) = f'_q(x - ex)                                shuffle + shared memory again
-//   store  A(x, y + ey, z + ez, q) = g_q(x)                      if cell x - ex is live (computes); full lines
-// The thread set {load addresses} == {store addresses} as before, so the update stays race free.  Where a row is
-// longer than a block (DIM > 256) the two threads at a block edge fall back to direct accesses of A(x -+ 1, ..) for
-// the five directions that leave the block, exactly as step_aa_kernel does for every thread (and the thread that
-// owns that aligned address skips it).  Two __syncthreads per block, 2 x 10 values per warp of shared memory.
-template <typename T, bool FAST, bool MACRO, int LM>
-__global__ void __launch_bounds__(256, aa_shift_min_blocks<T>()) step_aa_shift_aligned_kernel(const StepArgs<T> a)
-{
-    static_assert(LM == LM_ROWS || LM == LM_SOA || LM == LM_BLOCKROWS, "uniform row offsets needed");
-    // [round: 0 gather, 1 scatter][towards +x: value of lane 31 | towards -x: value of lane 0][k][warp]
-    __shared__ T edge[2][2][5][8];
-
-    const int dim = a.dim;
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    const int z = a.z_begin + blockIdx.z * blockDim.z + threadIdx.z;
-    const int rowbits = z < a.z_end ? row_bits(y, z, dim) : CT_WALL;
-    const bool row_live = rowbits != CT_WALL;                   // warp-uniform: a warp lies inside one row
-    const bool cell_live = row_live && x >= 1 && x <= dim - 2;  // WALL cells do not compute
-    const int lane = threadIdx.x & 31;
-    const int warp = (threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z)) >> 5;
-    const bool first_in_block = threadIdx.x == 0;               // lane 0 of the row segment's first warp
-    const bool last_in_block = threadIdx.x == blockDim.x - 1;   // lane 31 of its last warp
-
-    const long long plane = (long long)dim * dim;
-    const long long rowid = (long long)y * dim + (long long)(z - a.zs0) * plane;
-    const long long id0 = x + rowid;
-    long long b0;
-    long long nbc[9];
-    if constexpr (LM == LM_ROWS) {
-        b0 = rowid * Q + ((((x >> a.lay.sdiv) * Q) << a.lay.sdiv) + (x & (int)a.lay.smod));
-    } else if constexpr (LM == LM_SOA) {
-        b0 = id0;
-    } else {
-        b0 = a.lay.base(rowid) + x;
-        const int r = (y + (z - a.zs0) * dim) & a.row_mask;
-#pragma unroll
-        for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-            for (int dz = -1; dz <= 1; ++dz)
-                nbc[(dy + 1) * 3 + dz + 1] = (long long)((r - dy - dz * dim) >> a.row_shift) * a.blk18;
-    }
-    (void)nbc;
-    char *const c0 = reinterpret_cast<char *>(a.dst + b0);
-    // (x, y - ey, z - ez, opp(q)): what direction q is gathered from, at my own x
-    auto src_slot = [&](auto qc) -> T * {
-        constexpr int q = decltype(qc)::value;
-        if constexpr (LM == LM_BLOCKROWS) return reinterpret_cast<T *>(c0 + nbc[(ey(q) + 1) * 3 + ez(q) + 1] + a.goff[q]);
-        else return reinterpret_cast<T *>(c0 + a.goff[q]);
-    };
-    // (x, y + ey, z + ez, q): where direction q is pushed to, at my own x
-    auto dst_slot = [&](auto qc) -> T * {
-        constexpr int q = decltype(qc)::value;
-        if constexpr (LM == LM_BLOCKROWS) return reinterpret_cast<T *>(c0 + nbc[(-ey(q) + 1) * 3 - ez(q) + 1] + a.poff[q]);
-        else return reinterpret_cast<T *>(c0 + a.poff[q]);
-    };
-    // the address of element x + dx of the same run-of-a-row (dx = +-1): the neighbouring cell's slot
-    auto x_neighbour = [&](T *p, int dx) -> T * {
-        if constexpr (LM == LM_ROWS) {
-            const int xn = x + dx;
-            const long long bn = rowid * Q + ((((xn >> a.lay.sdiv) * Q) << a.lay.sdiv) + (xn & (int)a.lay.smod));
-            return p + (bn - b0);
-        } else {
-            return p + dx;
-        }
-    };
-
-    // ---- load at my own x ----
-    T f[Q];
-    if (row_live) {
-        static_for<Q>([&](auto qc) { f[decltype(qc)::value] = *src_slot(qc); });
-    } else {
-#pragma unroll
-        for (int q = 0; q < Q; ++q) f[q] = T(0);
-    }
-
-    // ---- gather round: f_q(x) = a_q(x - ex) ----
-    if (lane == 31) {
-#pragma unroll
-        for (int k = 0; k < 5; ++k) edge[0][0][k][warp] = f[aa_xp(k)];
-    }
-    if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < 5; ++k) edge[0][1][k][warp] = f[aa_xm(k)];
-    }
-    __syncthreads();
-    static_for<5>([&](auto kc) {
-        constexpr int k = decltype(kc)::value;
-        constexpr int qp = aa_xp(k), qm = aa_xm(k);
-        T vp = __shfl_up_sync(0xffffffffu, f[qp], 1);
-        T vm = __shfl_down_sync(0xffffffffu, f[qm], 1);
-        if (lane == 0) {
-            if (!first_in_block) vp = edge[0][0][k][warp - 1];
-            else if (cell_live) vp = *x_neighbour(src_slot(IntC<qp>{}), -1);
-        }
-        if (lane == 31) {
-            if (!last_in_block) vm = edge[0][1][k][warp + 1];
-            else if (cell_live) vm = *x_neighbour(src_slot(IntC<qm>{}), +1);
-        }
-        f[qp] = vp;
-        f[qm] = vm;
-    });
-
-    const T nan = static_cast<T>(__int_as_float(0x7fc00000));
-    T rho = nan, ux = nan, uy = nan, uz = nan;
-    int t = CT_WALL;
-    if (cell_live) t = aa_collide_cell<T, FAST>(a, f, rowbits, x, dim, rho, ux, uy, uz);
-
-    // ---- scatter round: g_q(x) = f'_q(x - ex), stored iff cell x - ex is live ----
-    if (lane == 31) {
-#pragma unroll
-        for (int k = 0; k < 5; ++k) edge[1][0][k][warp] = f[aa_xp(k)];
-    }
-    if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < 5; ++k) edge[1][1][k][warp] = f[aa_xm(k)];
-    }
-    // block edges: the value cannot reach the thread that owns the aligned address, so it is stored directly
-    if (cell_live && last_in_block && x + 1 <= dim - 1) {
-        static_for<5>([&](auto kc) {
-            constexpr int q = aa_xp(decltype(kc)::value);
-            *x_neighbour(dst_slot(IntC<q>{}), +1) = f[q];
-        });
-    }
-    if (cell_live && first_in_block && x - 1 >= 0) {
-        static_for<5>([&](auto kc) {
-            constexpr int q = aa_xm(decltype(kc)::value);
-            *x_neighbour(dst_slot(IntC<q>{}), -1) = f[q];
-        });
-    }
-    __syncthreads();
-    const bool from_left_live = row_live && x - 1 >= 1 && x - 1 <= dim - 2 && !first_in_block;   // cell x - 1 computes
-    const bool from_right_live = row_live && x + 1 >= 1 && x + 1 <= dim - 2 && !last_in_block;   // cell x + 1 computes
-    static_for<5>([&](auto kc) {
-        constexpr int k = decltype(kc)::value;
-        constexpr int qp = aa_xp(k), qm = aa_xm(k);
-        T gp = __shfl_up_sync(0xffffffffu, f[qp], 1);
-        T gm = __shfl_down_sync(0xffffffffu, f[qm], 1);
-        if (lane == 0 && !first_in_block) gp = edge[1][0][k][warp - 1];
-        if (lane == 31 && !last_in_block) gm = edge[1][1][k][warp + 1];
-        if (from_left_live) *dst_slot(IntC<qp>{}) = gp;
-        if (from_right_live) *dst_slot(IntC<qm>{}) = gm;
-    });
-    if (cell_live) {
-        static_for<Q>([&](auto qc) {
-            constexpr int q = decltype(qc)::value;
-            if constexpr (ex(q) == 0) *dst_slot(qc) = f[q];
-        });
-        if constexpr (MACRO) {
-            if (is_collision(t)) {
-                a.rho[id0] = rho;
-                a.u[id0] = ux;
-                a.u[a.n_local + id0] = uy;
-                a.u[2 * a.n_local + id0] = uz;
-            }
         }
     }
 }

@@ -17,7 +17,6 @@ struct LaunchCfg {
     int dim;
     int lm;           // LM_* addressing mode
     bool fast;        // -o
-    bool aa_unaligned = false;  // AA variant: the SHIFT step with per-thread x +- 1 accesses (cross-check / A-B)
 };
 
 // grid of a pull / AA launch over `n_planes` planes
@@ -45,14 +44,16 @@ cudaError_t launch_aa_f64(const LaunchCfg &, const StepArgs<double> &, bool macr
 
 // TMA-fed kernels (lbm_launch_tma.cu)
 struct TmaCfg {
-    const CUtensorMap *map_src;
-    const CUtensorMap *map_dst;
-    int tx;            // threads per CTA = cells per row tile
+    const CUtensorMap *map_src;   // load map of the lattice read
+    const CUtensorMap *map_dst;   // store map of the lattice written
+    int tx;            // cells per row tile = consumer threads per CTA (the CTA has tx + 32 threads)
     int grid;          // persistent CTAs
     size_t smem;       // dynamic shared memory per CTA
+    int osdiv;         // log2(min(stride, 32)): layout of a warp's output tile
     int *error;        // device flag: an mbarrier wait ran into its limit
     bool fast;
 };
+bool tma_direct_store();              // results leave through plain stores (else: per-warp bulk-tensor stores)
 cudaError_t tma_prepare(int device);  // once per device: opt in to > 48 KB dynamic shared memory
 int tma_resident_ctas(bool f64, int tx, size_t smem, bool fast);  // CTAs per SM by registers and shared memory
 cudaError_t launch_tma_f32(const TmaCfg &, const StepArgs<float> &, int ns, bool macro, cudaStream_t);

@@ -9,17 +9,6 @@ template <typename T, bool FAST, bool MACRO, bool SHIFT>
 void by_lm(const LaunchCfg &k, const StepArgs<T> &a, cudaStream_t s)
 {
     const dim3 g = step_grid(k, 1, a.z_end - a.z_begin), b = k.block;
-    if constexpr (SHIFT) {
-        // whole warps inside one row: every access aligned, x shifts by shuffle (step_aa_shift_aligned_kernel)
-        if (!k.aa_unaligned && b.x % 32 == 0 && k.lm != LM_GENERIC) {
-            switch (k.lm) {
-                case LM_ROWS: step_aa_shift_aligned_kernel<T, FAST, MACRO, LM_ROWS><<<g, b, 0, s>>>(a); break;
-                case LM_SOA: step_aa_shift_aligned_kernel<T, FAST, MACRO, LM_SOA><<<g, b, 0, s>>>(a); break;
-                default: step_aa_shift_aligned_kernel<T, FAST, MACRO, LM_BLOCKROWS><<<g, b, 0, s>>>(a); break;
-            }
-            return;
-        }
-    }
     switch (k.lm) {
         case LM_ROWS: step_aa_kernel<T, FAST, MACRO, SHIFT, LM_ROWS><<<g, b, 0, s>>>(a); break;
         case LM_SOA: step_aa_kernel<T, FAST, MACRO, SHIFT, LM_SOA><<<g, b, 0, s>>>(a); break;

@@ -28,7 +28,7 @@ template <typename T>
 void go(const TmaCfg &k, const TmaArgs<T> &a, bool macro, int grid, cudaStream_t s)
 {
     const CUtensorMap &ms = *k.map_src, &md = *k.map_dst;
-    const int tx = k.tx;
+    const int tx = k.tx + 32;  // consumers + the producer warp
     if (k.fast) {
         if (macro) step_tma_kernel<T, true, true><<<grid, tx, k.smem, s>>>(ms, md, a, k.error);
         else step_tma_kernel<T, true, false><<<grid, tx, k.smem, s>>>(ms, md, a, k.error);
@@ -47,6 +47,7 @@ cudaError_t launch_tma(const TmaCfg &k, const StepArgs<T> &sa, int ns, bool macr
     if (zl <= zf) return cudaSuccess;
     TmaArgs<T> a{};
     a.src = sa.src;
+    a.dst = sa.dst;
     a.rho = sa.rho;
     a.u = sa.u;
     a.dim = sa.dim;
@@ -55,6 +56,7 @@ cudaError_t launch_tma(const TmaCfg &k, const StepArgs<T> &sa, int ns, bool macr
     a.n_xseg = sa.dim / k.tx;
     a.n_tiles = (zl - zf) * (sa.dim - 2) * a.n_xseg;
     a.ns = ns;
+    a.osdiv = k.osdiv;
     a.n_local = sa.n_local;
     a.lay = sa.lay;
     a.c = sa.c;
@@ -71,11 +73,11 @@ int resident_ctas(int tx, size_t smem, bool fast)
     int n = 0, m = 0;
     cudaError_t e;
     if (fast) {
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, step_tma_kernel<T, true, false>, tx, smem);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m, step_tma_kernel<T, true, true>, tx, smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, step_tma_kernel<T, true, false>, tx + 32, smem);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m, step_tma_kernel<T, true, true>, tx + 32, smem);
     } else {
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, step_tma_kernel<T, false, false>, tx, smem);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m, step_tma_kernel<T, false, true>, tx, smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, step_tma_kernel<T, false, false>, tx + 32, smem);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m, step_tma_kernel<T, false, true>, tx + 32, smem);
     }
     if (e != cudaSuccess) {
         cudaGetLastError();
@@ -86,6 +88,9 @@ int resident_ctas(int tx, size_t smem, bool fast)
 }
 
 }  // namespace
+
+// Whether this build's TMA kernels store with plain coalesced stores (no output tiles in shared memory).
+bool tma_direct_store() { return LBM_TMA_DIRECT_STORE != 0; }
 
 // How many CTAs of the TMA kernels fit one SM (registers and shared memory): the persistent grid is exactly that
 // many per SM, so that it runs as ONE wave.

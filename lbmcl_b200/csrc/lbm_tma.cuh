@@ -1,4 +1,4 @@
-// TMA-fed variant of the D3Q19 step (sm_90+/sm_100a: cp.async.bulk.tensor + mbarrier).
+// TMA-fed variant of the D3Q19 step (sm_90+/sm_100a: cp.async.bulk.tensor + mbarrier), warp-specialised.
 //
 // Same function as step_pull_kernel (two-lattice pull, post-collision storage, see lbm_kernels.cuh);
 // what changes is how the bytes move:
@@ -6,17 +6,23 @@
 //   * the lattice is described to the TMA unit as a 3-D tensor  [block][q][stride]  (the CSoA layout of
 //     kernels.cl:64 read literally), so ONE bulk-tensor copy fetches the TX populations of one direction
 //     of one x-row segment -- whatever the stride -- into a contiguous shared-memory row;
-//   * persistent CTAs (a few per SM) walk the live rows of the launch; one elected thread keeps a ring of
-//     NS row-tiles in flight (19 bulk loads per tile, completion on an mbarrier with expect_tx);
-//   * every thread owns one cell: 19 conflict-free LDS at compile-time offsets (the x +- 1 shift is
-//     just an index), the reference's BC / collision, 19 STS into the same tile, and the elected
-//     thread sends the tile back with 19 bulk-tensor stores.
+//   * persistent CTAs (a few per SM) walk the live rows of the launch.  Each CTA is TX/32 CONSUMER warps (one
+//     thread per cell of a row tile) plus one PRODUCER warp whose elected lane keeps a ring of NS input tiles in
+//     flight: 19 bulk loads per tile, completion on the stage's `full` mbarrier (expect_tx); a stage is handed
+//     back through its `empty` mbarrier, on which every consumer warp arrives as soon as its 19 values are in
+//     registers -- the loads of tile i + NS are under way while tile i is still being collided;
+//   * a consumer reads its 19 populations with conflict-free LDS at compile-time offsets (the x +- 1 shift is
+//     just an index), applies the reference's BC / collision, and writes the results into its WARP's private
+//     output buffer, laid out as the warp's piece of the CSoA lattice ([q][32] for stride >= 32): one
+//     bulk-tensor store per warp and tile (19 x 128 bytes in fp32), double-buffered with
+//     cp.async.bulk.wait_group.read.  Consumer warps never meet at a CTA-wide barrier.
 //
-// Per cell this replaces 19 LDG + 19 STG + ~76 64-bit address instructions by 19 LDS + 19 STS with
-// immediate offsets, and decouples the HBM latency from the occupancy (the ring depth hides it).
+// Round 1's version of this kernel (one elected thread issuing 19 loads + 19 stores between two __syncthreads per
+// tile, tiles updated in place) was bound by that per-CTA critical path: 5.5 TB/s, profiles/r01_tma_experiment.md.
+//
 // Requirements (checked by the host): LM_ROWS layout (stride <= DIM), stride*sizeof(T) >= 16 bytes,
-// DIM >= 32.  Rows wider than TX = 256 cells are cut into segments; the two segment-edge threads fetch
-// their out-of-tile neighbour with a plain load.
+// DIM >= 32.  Rows wider than TX cells are cut into segments; the two segment-edge threads fetch their
+// out-of-tile neighbour with a plain load.
 #pragma once
 
 #include <cuda.h>
@@ -28,6 +34,7 @@ namespace lbm {
 template <typename T>
 struct TmaArgs {
     const T *__restrict__ src;  // for the segment-edge loads only
+    T *__restrict__ dst;        // direct-store build: the lattice written
     T *__restrict__ rho;
     T *__restrict__ u;
     int dim;
@@ -35,7 +42,8 @@ struct TmaArgs {
     int z_first;        // first live global plane of this launch (already clipped to [1, DIM-2])
     int n_tiles;        // live rows x segments of this launch
     int n_xseg;         // DIM / TX
-    int ns;             // ring depth
+    int ns;             // input ring depth
+    int osdiv;          // log2(S'), S' = min(stride, 32): a warp's output buffer is [32/S'][Q][S']
     long long n_local;
     Layout lay;
     Consts<T> c;
@@ -51,6 +59,10 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
 {
@@ -89,91 +101,141 @@ __device__ __forceinline__ void tma_wait_read()
 __device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// TX = cells per row tile = threads per CTA (32, 64, 128 or 256) is the launch's blockDim.x, not a template
-// parameter: the kernel exists once per (T, FAST, MACRO) instead of four times.
+// How the results leave the SM:
+//   LBM_TMA_DIRECT_STORE = 1 (default)  plain coalesced stores from registers (19 full lines per warp, as in
+//                                       step_pull_kernel): shared memory holds input tiles only, so three CTAs
+//                                       (24 consumer warps in fp32) fit an SM;
+//   LBM_TMA_DIRECT_STORE = 0            each consumer warp stages its 32 cells x 19 directions in a private,
+//                                       double-buffered tile laid out as its piece of the CSoA lattice and sends it
+//                                       with ONE bulk-tensor store (cp.async.bulk.wait_group.read before reuse):
+//                                       twice the shared memory per warp, two CTAs per SM.
+// Measured on B200 (profiles/r02_tma_experiment.md): the kernel is bound by the number of resident consumer
+// warps (the strict collision is one long dependency chain per thread), i.e. by shared memory per warp.
+#ifndef LBM_TMA_DIRECT_STORE
+#define LBM_TMA_DIRECT_STORE 1
+#endif
+#ifndef LBM_TMA_MINB
+#define LBM_TMA_MINB (LBM_TMA_DIRECT_STORE ? 3 : 2)
+#endif
+template <typename T>
+__host__ __device__ constexpr int tma_min_blocks()
+{
+    return sizeof(T) == 4 ? LBM_TMA_MINB : 2;
+}
+
+// Bounded mbarrier wait: a TMA fault or a protocol error must not hang the GPU.  Returns false when the limit
+// was hit or another warp of the CTA has already given up (`*abort_flag`).
+__device__ __forceinline__ bool mbar_wait_bounded(uint64_t *bar, uint32_t parity, volatile int *abort_flag)
+{
+    if (mbar_try_wait(bar, parity)) return true;
+    for (long long spins = 0; !mbar_try_wait(bar, parity); ++spins) {
+        if ((spins & 0x3ff) == 0x3ff && (*abort_flag != 0 || spins > (1ll << 22))) return false;
+    }
+    return true;
+}
+
+// blockDim.x = TX + 32: threads [0, TX) are the consumers (TX = cells per row tile: 32, 64, 128 or 256 -- the
+// launch's choice, not a template parameter), warp TX/32 is the producer.
 template <typename T, bool FAST, bool MACRO>
-__global__ void __launch_bounds__(256) step_tma_kernel(const __grid_constant__ CUtensorMap map_src,
-                                                        const __grid_constant__ CUtensorMap map_dst,
-                                                        const TmaArgs<T> a, int *__restrict__ error_flag)
+__global__ void __launch_bounds__(288, tma_min_blocks<T>()) step_tma_kernel(const __grid_constant__ CUtensorMap map_src,
+                                                                            const __grid_constant__ CUtensorMap map_dst,
+                                                                            const TmaArgs<T> a, int *__restrict__ error_flag)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int TX = (int)blockDim.x;
+    const int TX = (int)blockDim.x - 32;
+    const int NW = TX >> 5;  // consumer warps
     const uint32_t STAGE_BYTES = (uint32_t)(Q * TX * sizeof(T));
+    constexpr uint32_t OUT_BYTES = LBM_TMA_DIRECT_STORE ? 0u : (uint32_t)(Q * 32 * sizeof(T));  // one warp's output tile
     const int NS = a.ns;
-    T *const ring = reinterpret_cast<T *>(smem_raw);                                   // [NS][Q][TX]
-    uint64_t *const full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)NS * STAGE_BYTES);  // [NS]
+    T *const ring = reinterpret_cast<T *>(smem_raw);                                         // [NS][Q][TX]
+    T *const outb = reinterpret_cast<T *>(smem_raw + (size_t)NS * STAGE_BYTES);              // [NW][2][Q*32]
+    uint64_t *const full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)NS * STAGE_BYTES + (size_t)NW * 2 * OUT_BYTES);
+    uint64_t *const empty = full + NS;
+    int4 *const coords = reinterpret_cast<int4 *>(empty + NS);                               // [NS] (x0, y, z, -)
+    int *const abort_flag = reinterpret_cast<int *>(coords + NS);
+    (void)outb;
 
     const int tx = threadIdx.x;
+    const int warp = tx >> 5, lane = tx & 31;
     const int dim = a.dim;
-    const int rows = dim - 2;  // live y per plane
     const long long plane = (long long)dim * dim;
 
     if (tx == 0) {
-        for (int s = 0; s < NS; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], (uint32_t)NW);
+        }
+        *abort_flag = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
+    __syncthreads();  // the only CTA-wide barrier of the kernel
 
     const int n_my = a.n_tiles > (int)blockIdx.x ? (a.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
-    auto tile_coords = [&](int i, int &x0, int &y, int &z) {
-        const int t = (int)blockIdx.x + i * (int)gridDim.x;
-        const int xs = t % a.n_xseg;
-        const int r = t / a.n_xseg;
-        x0 = xs * TX;
-        y = 1 + r % rows;
-        z = a.z_first + r / rows;
-    };
-    // tensor coordinates of the TX values of direction q in row (yy, zz) starting at x0:
-    //   c0 = offset inside the CSoA run, c1 = q, c2 = CSoA block index
-    auto issue_loads = [&](int i) {
-        int x0, y, z;
-        tile_coords(i, x0, y, z);
-        const int s = i % NS;
-        mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
-        T *const dst = ring + (size_t)s * Q * TX;
-        const int c0 = x0 & (int)a.lay.smod;
-        const int xb = x0 >> a.lay.sdiv;
-        static_for<Q>([&](auto qc) {
-            constexpr int q = decltype(qc)::value;
-            const long long row = (long long)(y - ey(q)) * dim + (long long)(z - ez(q) - a.zs0) * plane;
-            tma_load_3d(dst + q * TX, &map_src, &full[s], c0, q, (int)(row >> a.lay.sdiv) + xb);
-        });
-    };
-
-    if (tx == 0) {
-        for (int i = 0; i < NS && i < n_my; ++i) issue_loads(i);
+    if (warp == NW) {
+        // ---------------- producer: one thread ----------------
+        if (lane != 0) return;
+        const int rows = dim - 2;  // live y per plane
+        for (int i = 0; i < n_my; ++i) {
+            const int s = i % NS;
+            if (i >= NS && !mbar_wait_bounded(&empty[s], (uint32_t)(i / NS - 1) & 1u, abort_flag)) {
+                *abort_flag = 1;
+                if (error_flag) atomicExch(error_flag, 1);
+                return;
+            }
+            // tile -> (row segment, y, z); the consumers read the coordinates from the stage
+            const int t = (int)blockIdx.x + i * (int)gridDim.x;
+            const int xs = t % a.n_xseg;
+            const int r = t / a.n_xseg;
+            const int x0 = xs * TX, y = 1 + r % rows, z = a.z_first + r / rows;
+            coords[s] = make_int4(x0, y, z, 0);
+            mbar_arrive_expect_tx(&full[s], STAGE_BYTES);  // release: orders the coordinates before the completion
+            T *const dst = ring + (size_t)s * Q * TX;
+            // tensor coordinates of the TX values of direction q in row (yy, zz) starting at x0:
+            //   c0 = offset inside the CSoA run, c1 = q, c2 = CSoA block index
+            const int c0 = x0 & (int)a.lay.smod;
+            const int xb = x0 >> a.lay.sdiv;
+            static_for<Q>([&](auto qc) {
+                constexpr int q = decltype(qc)::value;
+                const long long row = (long long)(y - ey(q)) * dim + (long long)(z - ez(q) - a.zs0) * plane;
+                tma_load_3d(dst + q * TX, &map_src, &full[s], c0, q, (int)(row >> a.lay.sdiv) + xb);
+            });
+        }
+        return;
     }
 
+    // ---------------- consumers: one thread per cell of the tile ----------------
     const T nan = static_cast<T>(__int_as_float(0x7fc00000));
+#if !LBM_TMA_DIRECT_STORE
+    T *const my_out = outb + (size_t)warp * 2 * (Q * 32);
+    // my slot inside the warp's output tile [32/S'][Q][S']
+    const int so = ((lane >> a.osdiv) * Q << a.osdiv) + (lane & ((1 << a.osdiv) - 1));
+    const int sq = 1 << a.osdiv;  // distance between consecutive q
+#endif
     for (int i = 0; i < n_my; ++i) {
-        int x0, y, z;
-        tile_coords(i, x0, y, z);
-        const int x = x0 + tx;
         const int s = i % NS;
-        const uint32_t parity = (uint32_t)(i / NS) & 1u;
-        T *const tile = ring + (size_t)s * Q * TX;
+        const T *const tile = ring + (size_t)s * Q * TX;
 
-        // bounded wait: a TMA fault must not hang the GPU.  A thread that runs into the limit carries on
-        // with whatever the tile holds; the CTA leaves together at the barrier below.
-        bool timed_out = false;
-        {
-            long long spins = 0;
-            while (!mbar_try_wait(&full[s], parity)) {
-                if (++spins > (1ll << 22)) {
-                    timed_out = true;
-                    break;
-                }
-            }
+        if (!mbar_wait_bounded(&full[s], (uint32_t)(i / NS) & 1u, abort_flag)) {
+            *abort_flag = 1;
+            if (lane == 0 && error_flag) atomicExch(error_flag, 1);
+            break;
         }
+        const int4 co = coords[s];
+        const int x0 = co.x, y = co.y, z = co.z;
+        const int x = x0 + tx;
 
         T f[Q];
         static_for<Q>([&](auto qc) {
             constexpr int q = decltype(qc)::value;
             f[q] = tile[q * TX + tx - ex(q)];  // tx -+ 1 outside the tile: fixed below (or a WALL cell)
         });
+        // this warp is done with the stage: hand it back to the producer
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+
+        const long long id0 = x + (long long)y * dim + (long long)(z - a.zs0) * plane;
         if (a.n_xseg > 1) {
-            const long long id0 = x + (long long)y * dim + (long long)(z - a.zs0) * plane;
             const long long qp = a.lay.qpitch();
             if (tx == 0 && x0 > 0) {
                 static_for<Q>([&](auto qc) {
@@ -210,11 +272,6 @@ __global__ void __launch_bounds__(256) step_tma_kernel(const __grid_constant__ C
                 });
             }
         }
-        // every thread has taken its inputs: the tile may be overwritten in place
-        if (__syncthreads_or(timed_out ? 1 : 0)) {  // CTA-uniform exit
-            if (tx == 0 && error_flag) atomicExch(error_flag, 1);
-            return;
-        }
 
         const int t = cell_type_from_row(rowbits, x, dim);
         T rho = nan, ux = nan, uy = nan, uz = nan;
@@ -228,32 +285,37 @@ __global__ void __launch_bounds__(256) step_tma_kernel(const __grid_constant__ C
         } else if (is_bounceback(t)) {
             bounce_back<T>(f);
         }
-        static_for<Q>([&](auto qc) {
-            constexpr int q = decltype(qc)::value;
-            tile[q * TX + tx] = f[q];
-        });
-        fence_proxy_async();  // generic-proxy writes -> visible to the bulk-copy (async) proxy
-        __syncthreads();
 
-        if (tx == 0) {
-            const int c0 = x0 & (int)a.lay.smod;
-            const long long row = (long long)y * dim + (long long)(z - a.zs0) * plane;
-            const int c2 = (int)(row >> a.lay.sdiv) + (x0 >> a.lay.sdiv);
+#if LBM_TMA_DIRECT_STORE
+        {
+            char *const d0 = reinterpret_cast<char *>(a.dst + a.lay.base(id0));
+            const long long qs = a.lay.qpitch() * (long long)sizeof(T);
             static_for<Q>([&](auto qc) {
                 constexpr int q = decltype(qc)::value;
-                tma_store_3d(&map_dst, tile + q * TX, c0, q, c2);
+                *reinterpret_cast<T *>(d0 + q * qs) = f[q];
             });
-            tma_commit();
-            // the stage of the previous tile is free once its stores have read shared memory
-            if (i >= 1 && i - 1 + NS < n_my) {
-                tma_wait_read<1>();
-                issue_loads(i - 1 + NS);
-            }
         }
+#else
+        // the bulk store that last read this output buffer (tile i - 2) must have finished reading it
+        T *const ob = my_out + (i & 1) * (Q * 32);
+        if (lane == 0) tma_wait_read<1>();
+        __syncwarp();
+        static_for<Q>([&](auto qc) {
+            constexpr int q = decltype(qc)::value;
+            ob[so + q * sq] = f[q];
+        });
+        fence_proxy_async();  // generic-proxy writes -> visible to the bulk-copy (async) proxy
+        __syncwarp();
+        if (lane == 0) {
+            const int xw = x0 + (warp << 5);  // the warp's first cell
+            const long long row = (long long)y * dim + (long long)(z - a.zs0) * plane;
+            tma_store_3d(&map_dst, ob, xw & (int)a.lay.smod, 0, (int)((row + xw) >> a.lay.sdiv));
+            tma_commit();
+        }
+#endif
 
         if constexpr (MACRO) {
             if (!(rowbits & (CT_TOP | CT_BOTTOM | CT_BACK))) {
-                const long long id0 = x + (long long)y * dim + (long long)(z - a.zs0) * plane;
                 a.rho[id0] = rho;
                 a.u[id0] = ux;
                 a.u[a.n_local + id0] = uy;
@@ -261,7 +323,9 @@ __global__ void __launch_bounds__(256) step_tma_kernel(const __grid_constant__ C
             }
         }
     }
-    if (tx == 0) tma_wait_all();
+#if !LBM_TMA_DIRECT_STORE
+    if (lane == 0) tma_wait_all();
+#endif
 }
 
 }  // namespace lbm

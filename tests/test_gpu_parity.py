@@ -124,20 +124,18 @@ def test_generic_addressing_equals_fast_addressing(variant, precision):
 
 @pytest.mark.parametrize("precision", ["f32", "f64"])
 @pytest.mark.parametrize("dim,stride,block", [
-    (64, 32, None),            # two warps per row: the x shift crosses a warp edge through shared memory
-    (64, 32, (32, 8, 1)),      # one warp per block, two blocks per row: block edges use the direct accesses
-    (128, 32, (64, 4, 1)),     # warp edges AND block edges inside a row
+    (64, 32, None),            # two warps per row
+    (64, 32, (32, 8, 1)),      # one warp per block, two blocks per row
+    (128, 32, (64, 4, 1)),     # warp edges and block edges inside a row
     (64, 64, None),            # stride == DIM
     (64, 512, None),           # LM_BLOCKROWS (a CSoA block holds 8 rows)
     (64, 262144, None),        # LM_SOA
     (32, 8, None),             # stride < warp: a warp's 32 cells span four CSoA runs
 ])
-def test_aa_shift_step_aligned_and_unaligned_kernels_match_the_oracle(dim, stride, block, precision):
-    """The in-place variant's SHIFT step exists in two forms: every thread accessing x +- 1 itself
-    (step_aa_kernel<SHIFT>, the round-1 kernel, now the cross-check) and the aligned form that moves values
-    between lanes by shuffle / shared memory (step_aa_shift_aligned_kernel, default).  Both must reproduce the
-    oracle bit for bit: rho/u snapshots and the complete -f view (which also shows the pushes into WALL cells),
-    after an even and an odd number of iterations."""
+def test_in_place_variant_rows_wider_than_a_warp_or_a_block(dim, stride, block, precision):
+    """The in-place variant on rows that span several warps / several blocks, for every addressing mode: rho/u
+    snapshots and the complete -f view (which also shows the pushes into WALL cells) against the oracle, after
+    an even and an odd number of iterations (LOCAL and SHIFT steps)."""
     every = 2
     kw = dict(dim=dim, precision=precision, stride=stride, variant=8)
     if block is not None:
@@ -146,12 +144,11 @@ def test_aa_shift_step_aligned_and_unaligned_kernels_match_the_oracle(dim, strid
         exp = Oracle(precision).run(dim, stride, 0.0089, 0.05, its, every, keep_state=True)
         st = exp["state"]
         want_f = (st["f_stream"] if (its + 1) % 2 == 0 else st["f_collide"]).tobytes()
-        for unaligned in (False, True):
-            with _sim(aa_unaligned_shift=unaligned, **kw) as s:
-                rho, u = s.run_snapshots(its, every)
-                got_f = s.read_f()
-            assert rho.tobytes() == exp["rho"].tobytes() and u.tobytes() == exp["u"].tobytes(), (its, unaligned)
-            assert got_f.tobytes() == want_f, (its, unaligned)
+        with _sim(**kw) as s:
+            rho, u = s.run_snapshots(its, every)
+            got_f = s.read_f()
+        assert rho.tobytes() == exp["rho"].tobytes() and u.tobytes() == exp["u"].tobytes(), its
+        assert got_f.tobytes() == want_f, its
 
 
 def test_step_api_equals_run_api():
