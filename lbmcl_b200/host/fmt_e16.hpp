@@ -25,12 +25,16 @@ struct U256 {
 
 struct Pow10Table {
     static constexpr int KMAX = 61;  // 53 + ceil(61 * log2(10)) = 256 bits
+    static constexpr int DMIN = -46, DMAX = 17;
     U256 p[KMAX + 1];
+    int limbs[KMAX + 1];             // non-zero 64-bit words of p[k]
+    double dec[DMAX - DMIN + 1];     // 10^d as a double (nearest), d = DMIN .. DMAX: only steers the first guess
     Pow10Table()
     {
         U256 v = {{1, 0, 0, 0}};
         for (int k = 0; k <= KMAX; ++k) {
             p[k] = v;
+            limbs[k] = v.w[3] ? 4 : v.w[2] ? 3 : v.w[1] ? 2 : 1;
             u128 carry = 0;
             for (int i = 0; i < 4; ++i) {
                 const u128 t = (u128)v.w[i] * 10u + carry;
@@ -38,6 +42,7 @@ struct Pow10Table {
                 carry = t >> 64;
             }
         }
+        for (int d = DMIN; d <= DMAX; ++d) dec[d - DMIN] = std::pow(10.0, d);
     }
 };
 
@@ -75,21 +80,29 @@ inline int fmt_e16(double v, char *out)
     if (bexp == 0 || bexp == 0x7ff || s < 1 || s > 255) return std::snprintf(out, 32, "%.16e", v);
     const uint64_t m = frac | (1ull << 52);
     // decimal exponent estimate from the binary one: floor(log10(m * 2^-s)), possibly one too small
-    // (m in [2^52, 2^53) => log10(v) in [(52 - s) * log10(2), (53 - s) * log10(2)))
-    int d = (int)std::floor((52 - s) * 0.30102999566398120);
+    // (m in [2^52, 2^53) => log10(v) in [(52 - s) * log10(2), (53 - s) * log10(2))); a comparison with 10^(d+1) as a
+    // double settles it except within an ulp of a power of ten, where the range check below corrects the guess
+    const Pow10Table &tab = pow10_table();
+    int d = ((52 - s) * 78913) >> 18;  // floor((52 - s) * log10(2)), exact for |52 - s| < 1650 (arithmetic shift)
+    if (d + 1 >= Pow10Table::DMIN && d + 1 <= Pow10Table::DMAX && std::fabs(v) >= tab.dec[d + 1 - Pow10Table::DMIN]) ++d;
     uint64_t q = 0;
     bool round_bit = false, sticky = false;
     for (int attempt = 0;; ++attempt) {
         const int k = 16 - d;
         if (k < 0 || k > Pow10Table::KMAX || attempt > 2) return std::snprintf(out, 32, "%.16e", v);
-        const U256 &pw = pow10_table().p[k];
-        // N = m * 10^k  (fits 256 bits for k <= KMAX)
-        uint64_t n[4];
-        u128 carry = 0;
-        for (int i = 0; i < 4; ++i) {
-            const u128 t = (u128)pw.w[i] * m + carry;
-            n[i] = (uint64_t)t;
-            carry = t >> 64;
+        const U256 &pw = tab.p[k];
+        // N = m * 10^k  (fits 256 bits for k <= KMAX); only the non-zero words of 10^k are multiplied
+        uint64_t n[4] = {0, 0, 0, 0};
+        {
+            const int nl = tab.limbs[k];
+            u128 carry = 0;
+            int i = 0;
+            for (; i < nl; ++i) {
+                const u128 t = (u128)pw.w[i] * m + carry;
+                n[i] = (uint64_t)t;
+                carry = t >> 64;
+            }
+            if (i < 4) n[i] = (uint64_t)carry;
         }
         // q = N >> s  (17 digits => fits 64 bits when d is right; detect overflow of that assumption)
         const int li = s >> 6, off = s & 63;
@@ -126,28 +139,23 @@ inline int fmt_e16(double v, char *out)
     }
     // 17 digits: D.DDDDDDDDDDDDDDDD
     if (neg) *p++ = '-';
-    char dig[17];
+    // q = h dddddddd dddddddd: the two 8-digit halves are converted independently, four digit pairs each
     const char *pairs = digit_pairs();
-    uint64_t hi = q / 100000000ull;           // 9 digits
-    uint32_t lo = (uint32_t)(q % 100000000ull);  // 8 digits
-    for (int i = 15; i >= 9; i -= 2) {
-        const uint32_t r = lo % 100;
-        lo /= 100;
-        dig[i] = pairs[2 * r];
-        dig[i + 1] = pairs[2 * r + 1];
-    }
-    uint32_t h = (uint32_t)hi;
-    for (int i = 7; i >= 1; i -= 2) {
-        const uint32_t r = h % 100;
-        h /= 100;
-        dig[i] = pairs[2 * r];
-        dig[i + 1] = pairs[2 * r + 1];
-    }
-    dig[0] = (char)('0' + h);
-    *p++ = dig[0];
-    *p++ = '.';
-    std::memcpy(p, dig + 1, 16);
-    p += 16;
+    const uint64_t top = q / 10000000000000000ull;                // leading digit
+    const uint64_t rest = q - top * 10000000000000000ull;         // 16 digits
+    const uint32_t a = (uint32_t)(rest / 100000000ull), b = (uint32_t)(rest % 100000000ull);
+    const uint32_t a1 = a / 10000, a0 = a % 10000, b1 = b / 10000, b0 = b % 10000;
+    p[0] = (char)('0' + top);
+    p[1] = '.';
+    std::memcpy(p + 2, pairs + 2 * (a1 / 100), 2);
+    std::memcpy(p + 4, pairs + 2 * (a1 % 100), 2);
+    std::memcpy(p + 6, pairs + 2 * (a0 / 100), 2);
+    std::memcpy(p + 8, pairs + 2 * (a0 % 100), 2);
+    std::memcpy(p + 10, pairs + 2 * (b1 / 100), 2);
+    std::memcpy(p + 12, pairs + 2 * (b1 % 100), 2);
+    std::memcpy(p + 14, pairs + 2 * (b0 / 100), 2);
+    std::memcpy(p + 16, pairs + 2 * (b0 % 100), 2);
+    p += 18;
     *p++ = 'e';
     int ad = d;
     if (ad < 0) {

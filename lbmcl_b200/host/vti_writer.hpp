@@ -72,31 +72,36 @@ inline void write_at(const Sink &k, const char *p, size_t n, size_t off)
     }
 }
 
-// one z-plane of one array as text (pass 0: rho, pass 1: v)
+// one z-plane of one array as text (pass 0: rho, pass 1: v); `out` is scratch storage that only ever grows,
+// the return value is the number of bytes written to its beginning
 template <typename T>
-void format_plane(std::string &out, size_t dim, int pass, size_t z, const T *rho, const T *u)
+size_t format_plane(std::string &out, size_t dim, int pass, size_t z, const T *rho, const T *u)
 {
     const size_t from = 1, to = dim - 1, n = dim * dim * dim;
-    out.clear();
-    out.reserve((to - from) * (to - from) * (pass == 0 ? 25 : 75) + dim);
-    char tmp[3 * 32];
+    // formatted straight into the string's storage: at most 25 characters per value + one newline per row
+    const size_t w = to - from;
+    const size_t bound = w * (w * (pass == 0 ? 1 : 3) * 25 + 1) + 32;
+    if (out.size() < bound) out.resize(bound);
+    char *const begin = &out[0];
+    char *p = begin;
     for (size_t y = from; y < to; ++y) {
-        for (size_t x = from; x < to; ++x) {
-            const size_t id = x + y * dim + z * dim * dim;
-            int len = 0;
-            if (pass == 0) {
-                len = lbm_fmt::fmt_e16((double)rho[id], tmp);
-                tmp[len++] = ' ';
-            } else {
+        const size_t row = y * dim + z * dim * dim;
+        if (pass == 0) {
+            for (size_t x = from; x < to; ++x) {
+                p += lbm_fmt::fmt_e16((double)rho[row + x], p);
+                *p++ = ' ';
+            }
+        } else {
+            for (size_t x = from; x < to; ++x) {
                 for (size_t c = 0; c < 3; ++c) {
-                    len += lbm_fmt::fmt_e16((double)u[c * n + id], tmp + len);
-                    tmp[len++] = ' ';
+                    p += lbm_fmt::fmt_e16((double)u[c * n + row + x], p);
+                    *p++ = ' ';
                 }
             }
-            out.append(tmp, (size_t)len);
         }
-        out += '\n';
+        *p++ = '\n';
     }
+    return (size_t)(p - begin);
 }
 
 // One array of the file, starting at byte `base`; returns the new end of the file.
@@ -113,16 +118,14 @@ size_t write_array(const Sink &fd, size_t base, size_t dim, int pass, const T *r
         size_t my_base = base;
         for (size_t r = 0; r < rounds; ++r) {
             const size_t k = r * nthreads + j;
-            if (k < planes) format_plane<T>(text[j], dim, pass, 1 + k, rho, u);
-            else text[j].clear();
-            size[j] = text[j].size();
+            size[j] = k < planes ? format_plane<T>(text[j], dim, pass, 1 + k, rho, u) : 0;
             bar.wait();  // every size of this round is known
             size_t before = 0, total = 0;
             for (unsigned i = 0; i < nthreads; ++i) {
                 if (i < j) before += size[i];
                 total += size[i];
             }
-            write_at(fd, text[j].data(), text[j].size(), my_base + before);
+            write_at(fd, text[j].data(), size[j], my_base + before);
             my_base += total;
             bar.wait();  // everybody has read the sizes: they may be overwritten
         }
