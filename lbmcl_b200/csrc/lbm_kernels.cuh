@@ -657,7 +657,7 @@ __device__ __forceinline__ void step_pull_body(const StepArgs<T> &a)
 }
 
 // Occupancy.  The step kernel is latency-bound as much as bandwidth-bound: its throughput follows the number
-// of resident warps (measured, profiles/r02_occupancy.md: the same code at 72 instead of 40 registers per
+// of resident warps (measured, profiles/r02_experiments.md section 1: the same code at 72 instead of 40 registers per
 // thread -- 3 instead of 6 blocks per SM -- runs 22 % slower), so the register budget is pinned per variant
 // instead of being left to ptxas' heuristics:
 //   fp32, 1 cell/thread     6 blocks of 256 threads per SM (40 registers; the kernel needs exactly that);
