@@ -9,6 +9,7 @@
 
 #include <cmath>
 #include <cstdlib>
+#include <cstdio>
 #include <cstring>
 #include <new>
 
@@ -135,6 +136,19 @@ StepArgs<T> make_step_args(lbm_ctx *c, const Planes &pl, int peer_mode, const Co
     a.z_end = pl.z_end;
     a.n_local = c->n_local;
     a.lay = c->lay;
+    // tile order of the blocks: only for launches over one contiguous plane range whose grid the tiles divide
+    a.swz_y = a.swz_z = -1;
+    a.swz_nty = 0;
+    const bool shift_step = c->aa && ((c->iteration + 1) % 2) == 0;
+    if (c->swz_z >= 0 && pl.n_named == 0 && (!c->swz_shift_only || shift_step)) {
+        const int ny = c->dim / (int)c->block.y, planes = pl.z_end - pl.z_begin;
+        const int nzb = planes / (int)c->block.z;
+        if (planes % (int)c->block.z == 0 && ny % (1 << c->swz_y) == 0 && nzb > 0 && nzb % (1 << c->swz_z) == 0) {
+            a.swz_y = c->swz_y;
+            a.swz_z = c->swz_z;
+            a.swz_nty = ilog2(ny >> c->swz_y);
+        }
+    }
     a.row_shift = c->lay.sdiv > ilog2(c->dim) ? c->lay.sdiv - ilog2(c->dim) : 0;
     a.row_mask = (1 << a.row_shift) - 1;
     a.blk18 = 18ll * c->lay.qpitch() * (long long)sizeof(T);
@@ -1002,6 +1016,26 @@ int lbm_create(const lbm_params *p, lbm_ctx **out)
     while (vec > 1 && (p->stride % vec != 0 || p->dim % vec != 0)) vec /= 2;
     c->vec = vec;
     choose_block(c);
+    // block order (lbm_kernels.cuh, block_yz).  Measured on B200 (profiles/r02_experiments.md section 6): the tile
+    // order helps exactly one kernel -- the SHIFT step of the in-place variant on lattices whose planes span several
+    // waves of blocks (1024^3: 28.08 -> 26.67 ms with tiles of 32 rows x 16 planes) -- and costs the kernels that
+    // stream whole rows (pull: -2.7 % at 512^3, LOCAL step: +4 %).  So: SHIFT launches at DIM >= 512 only.
+    // LBM_BLOCK_SWIZZLE="ly,lz" (log2 extents) forces a tile order on every step launch, "0" disables it.
+    if (c->aa && c->dim >= 512) {
+        c->swz_y = 5;
+        c->swz_z = 4;
+        c->swz_shift_only = true;
+    }
+    if (const char *e = std::getenv("LBM_BLOCK_SWIZZLE")) {
+        int ly = -1, lz = -1;
+        if (std::sscanf(e, "%d,%d", &ly, &lz) == 2 && ly >= 0 && lz >= 0 && ly + lz <= 20) {
+            c->swz_y = ly;
+            c->swz_z = lz;
+            c->swz_shift_only = false;
+        } else {
+            c->swz_y = c->swz_z = -1;
+        }
+    }
 
     if (const char *t = std::getenv("LBM_SYNC_TIMEOUT_S")) {
         const double s = std::atof(t);

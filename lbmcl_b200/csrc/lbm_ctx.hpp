@@ -49,6 +49,8 @@ struct lbm_ctx {
     int layout_mode = lbm::LM_GENERIC;     // what non-peer launches use (test hook: may be LM_GENERIC)
     int layout_natural = lbm::LM_GENERIC;  // what stride and DIM call for
     bool aa = false;             // in-place AA variant: only f[0] exists
+    int swz_y = -1, swz_z = -1;  // block order of the step kernels (block_yz): log2 tile extents, < 0 = grid order
+    bool swz_shift_only = false; // ... applied to the in-place variant's SHIFT launches only
     bool tma = false;            // TMA-fed variant: tensor maps of the two lattices
     CUtensorMap tmap[2];         // loads: box = one direction of one row tile
     CUtensorMap tmap_st[2];      // stores: box = one warp's 32 cells x 19 directions

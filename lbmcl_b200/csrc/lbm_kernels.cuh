@@ -72,6 +72,9 @@ struct StepArgs {
     // starts -- then the contiguous range [z_begin, z_end)
     int zmap_n, zmap0, zmap1;
     int z_begin, z_end;
+    // block order (block_yz): log2 of the tile's extent in block rows / block planes and of the number of tiles
+    // along y; swz_z < 0: the grid's own order
+    int swz_y, swz_z, swz_nty;
     long long n_local;          // cells in local storage (pitch of the u components)
     Layout lay;
     // LM_BLOCKROWS (DIM < stride): a CSoA block holds 2^row_shift whole x-rows
@@ -368,6 +371,25 @@ __device__ __forceinline__ void slab_signal(unsigned *count, unsigned n_blocks, 
     }
 }
 
+// Block order.  CUDA hands out the blocks of a grid x-fastest, then y, then z: plane by plane.  On a large lattice
+// one plane is several waves of blocks, so the rows of the planes z -+ 1 that a block gathers from (10 of the 19
+// populations) are touched again only thousands of blocks later -- each DRAM page of those planes is opened for
+// a quarter of its bytes now and for the rest much later.  With a tile order the (y, z) pairs are walked in tiles
+// of 2^swz_y block rows x 2^swz_z block planes (y fastest inside a tile, tiles along y first), so that most
+// y -+ 1 AND z -+ 1 neighbours of a block are in flight in the same wave.  A bijection on the grid's (y, z) block
+// indices as long as gridDim.y is a multiple of 2^swz_y and gridDim.z of 2^swz_z (the host checks).
+__device__ __forceinline__ void block_yz(const int swz_y, const int swz_z, const int swz_nty, int &by, int &bz)
+{
+    by = (int)blockIdx.y;
+    bz = (int)blockIdx.z;
+    if (swz_z >= 0) {
+        const unsigned l = blockIdx.y + gridDim.y * blockIdx.z;
+        const unsigned w = l & ((1u << (swz_y + swz_z)) - 1u), t = l >> (swz_y + swz_z);
+        by = (int)(((t & ((1u << swz_nty) - 1u)) << swz_y) + (w & ((1u << swz_y) - 1u)));
+        bz = (int)(((t >> swz_nty) << swz_z) + (w >> swz_y));
+    }
+}
+
 // One cell-group of one iteration: the thread owns the VEC cells x0 .. x0+VEC-1 of row (y, z).
 // `mask` = the lanes of the warp that execute this function (shuffles of the VEC > 1 variants).
 template <typename T, int VEC, bool FAST, bool MACRO, int PEER, int LM>
@@ -611,8 +633,10 @@ __device__ __forceinline__ void step_pull_body(const StepArgs<T> &a)
 {
     const int dim = LBM_U_DIM(a);
     const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    const int zi = blockIdx.z * blockDim.z + threadIdx.z;
+    int by, bz;
+    block_yz(a.swz_y, a.swz_z, a.swz_nty, by, bz);
+    const int y = by * blockDim.y + threadIdx.y;
+    const int zi = bz * blockDim.z + threadIdx.z;
     int z;
     bool zok = true;
     if (zi < a.zmap_n) {
@@ -756,8 +780,10 @@ __global__ void __launch_bounds__(256, aa_min_blocks<T, SHIFT>()) step_aa_kernel
 {
     const int dim = a.dim;
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    const int z = a.z_begin + blockIdx.z * blockDim.z + threadIdx.z;
+    int by, bz;
+    block_yz(a.swz_y, a.swz_z, a.swz_nty, by, bz);
+    const int y = by * blockDim.y + threadIdx.y;
+    const int z = a.z_begin + bz * blockDim.z + threadIdx.z;
     if (z >= a.z_end) return;
     const int rowbits = row_bits(y, z, dim);
     if (rowbits == CT_WALL || x == 0 || x >= dim - 1) return;  // WALL cells neither read nor write
