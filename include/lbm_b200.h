@@ -52,10 +52,10 @@ typedef enum lbm_variant {
     LBM_VARIANT_VEC4 = 4,   /* two-lattice pull, 4 cells per thread (128-bit fp32 access)        */
     LBM_VARIANT_AA = 8,     /* in-place AA pattern: ONE lattice (half the memory), one cell per
                                thread; whole cube on one device only                             */
-    LBM_VARIANT_TMA = 16,   /* two-lattice pull fed by the TMA unit: persistent CTAs, bulk-tensor
-                               loads into an mbarrier ring of row tiles, bulk-tensor stores back;
-                               needs stride <= DIM, stride*sizeof(T) >= 16, DIM >= 32 (else the
-                               scalar variant is used)                                           */
+    LBM_VARIANT_TMA = 16,   /* two-lattice pull fed by the TMA unit, warp-specialised: persistent CTAs of
+                               consumer warps + one producer warp that keeps a ring of row tiles in flight
+                               (bulk-tensor loads, full/empty mbarrier pairs); needs stride <= DIM,
+                               stride*sizeof(T) >= 16, DIM >= 32 (else the scalar variant is used)  */
     LBM_VARIANT_NVRTC = 32  /* the scalar kernel compiled at run time (NVRTC) with DIM, stride, the
                                address offsets, INV_TAU and U as literals -- what the reference does
                                with its -D kernel options (lbmcl.hpp:131-156, CLUtil.hpp:201-229);
