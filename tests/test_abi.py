@@ -95,3 +95,24 @@ def test_specialised_kernel_source_builds_without_a_gpu():
         cubin = capi.spec_cubin(**kw)
         assert cubin[:4] == b"\x7fELF" and len(cubin) > 10000
         assert b"lbm_step_spec_m0" in cubin and b"lbm_step_spec_m1" in cubin
+
+
+def test_compile_time_alternatives_of_the_kernels_still_build(tmp_path):
+    """The measured-and-not-adopted forms stay in the sources behind compile-time knobs (profiles/r02_*.md): the TMA
+    kernel with per-warp bulk-tensor stores, other register budgets.  They must keep compiling for sm_100a (nvcc
+    cross-compiles without a GPU) so that the A/B builds of the profiles can be reproduced."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    src = os.path.join(ROOT, "lbmcl_b200", "csrc")
+    base = [nvcc, "-std=c++17", "-O1", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-c"]
+    for name, unit, flags in (
+            ("tma_bulk_store", "lbm_launch_tma.cu", ["-DLBM_TMA_DIRECT_STORE=0"]),
+            ("aa_shift_40_registers", "lbm_launch_aa.cu", ["-DLBM_MINB_AA_SHIFT_F32=6"])):
+        r = subprocess.run(base + flags + ["-o", str(tmp_path / (name + ".o")), os.path.join(src, unit)],
+                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+        assert r.returncode == 0, f"{name}: {r.stdout[-3000:]}"
+    out = subprocess.run(["cuobjdump", "-sass", str(tmp_path / "tma_bulk_store.o")], stdout=subprocess.PIPE, text=True).stdout
+    assert "UTMALDG" in out and "UTMASTG" in out       # bulk-tensor loads AND stores in that build
+    lib = subprocess.run(["cuobjdump", "-sass", os.path.join(src, "liblbm_b200.so")], stdout=subprocess.PIPE, text=True).stdout
+    assert "UTMALDG" in lib and "SYNCS" in lib         # the shipped TMA kernel: bulk-tensor loads + mbarriers
